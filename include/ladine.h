@@ -1,0 +1,159 @@
+/*
+ * ladine.h -- C ABI of the B200-native LaDiNE nested-ensemble reverse-diffusion sampler.
+ *
+ * The reference (xingbpshen/nested-diffusion) is pure Python and has no FFI for this path; the
+ * boundary it offers is the Python call
+ *     diffusion_utils.p_sample_loop(model, x, y_0_hat, y_T_mean, n_steps, alphas,
+ *                                   one_minus_alphas_bar_sqrt, only_last_sample=...)   (diffusion_utils.py:133-163)
+ * driven K x 20 times per test batch by classification_train_separately.py:764-784.  This header is
+ * what a ctypes / cffi / cgo / JNI stub would bind to replace that call chain; the Python mirror in
+ * nested_diffusion_b200/ binds it with ctypes.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every pointer is a raw CUDA device pointer unless marked HOST;
+ *   - all tensors are FP32, dense, row-major, in the layouts of the reference's tensors;
+ *   - every call returns 0 on success or a negative ladine_status; nothing throws across the ABI;
+ *     ladine_last_error() returns a human-readable message for the last failure on that handle;
+ *   - work is enqueued on the caller's CUDA stream (cudaStream_t passed as void*); pointers are
+ *     borrowed until that stream-ordered work completes; no hidden host synchronisation;
+ *   - a handle is bound to one device and is not re-entrant (the caller serialises calls per
+ *     handle); distinct handles are independent.
+ */
+#ifndef LADINE_H_
+#define LADINE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LADINE_ABI_VERSION 1
+#define LADINE_MAX_CLASSES 16   /* num_classes supported by the fused kernels            */
+#define LADINE_MAX_GROUP   8    /* members fused into one launch group (larger K loops)  */
+
+typedef struct ladine_handle ladine_handle;
+typedef struct ladine_member ladine_member;
+
+typedef enum {
+  LADINE_OK = 0,
+  LADINE_ERR_INVALID = -1,     /* bad argument (shape, null pointer, range)              */
+  LADINE_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed                    */
+  LADINE_ERR_UNSUPPORTED = -3, /* valid in the reference but not accelerated here        */
+  LADINE_ERR_NOMEM = -4        /* workspace allocation failed                            */
+} ladine_status;
+
+typedef enum {
+  LADINE_PREC_AUTO = 0, /* FP32 SMEM-resident kernel when feature_dim <= 128, else FP16 tensor cores */
+  LADINE_PREC_FP32 = 1, /* FP32 FFMA, weights resident in shared memory (feature_dim <= 128)         */
+  LADINE_PREC_FP16 = 2, /* tcgen05 kind::f16, FP16 operands, FP32 accumulate in TMEM                 */
+  LADINE_PREC_BF16 = 3  /* tcgen05 kind::f16, BF16 operands, FP32 accumulate in TMEM                 */
+} ladine_precision;
+
+/*
+ * One ensemble member = the trunk of one latent_model.ConditionalModel (latent_model.py:155-184):
+ * lin1..lin3 (ConditionalLinear: nn.Linear + nn.Embedding gamma table, latent_model.py:93-105),
+ * unetnorm1..3 (BatchNorm1d, eval mode) and lin4.  Pointers are the module's own parameter
+ * tensors (state_dict keys in the comments); the library folds and re-lays them out into buffers
+ * it owns, so they may be freed after ladine_pack_member returns and the stream is synchronised.
+ * The image encoder (encoder_x + norm) is step-invariant and is evaluated by the caller: see xf.
+ */
+typedef struct {
+  uint32_t struct_size;   /* sizeof(ladine_member_desc)                                  */
+  int32_t feature_dim;    /* F: config.model.feature_dim                                 */
+  int32_t num_classes;    /* C: config.data.num_classes (<= LADINE_MAX_CLASSES)          */
+  int32_t n_steps;        /* T: rows of the gamma tables the sampler may index (0..T-1)  */
+  int32_t emb_rows;       /* rows actually present in lin*.embed.weight (>= T; T+1 in the reference) */
+  int32_t guidance;       /* 1: lin1 takes cat(y, y_0_hat) [2C]; 0: y only [C]            */
+  int32_t precision;      /* ladine_precision                                            */
+  float bn_eps;           /* BatchNorm1d eps (1e-5)                                      */
+  const float* lin1_w;    /* lin1.lin.weight  [F, 2C or C]                               */
+  const float* lin1_b;    /* lin1.lin.bias    [F]                                        */
+  const float* lin2_w;    /* lin2.lin.weight  [F, F]                                     */
+  const float* lin2_b;    /* lin2.lin.bias    [F]                                        */
+  const float* lin3_w;    /* lin3.lin.weight  [F, F]                                     */
+  const float* lin3_b;    /* lin3.lin.bias    [F]                                        */
+  const float* lin4_w;    /* lin4.weight      [C, F]                                     */
+  const float* lin4_b;    /* lin4.bias        [C]                                        */
+  const float* emb[3];    /* lin{1,2,3}.embed.weight [emb_rows, F]                       */
+  const float* bn_w[3];   /* unetnorm{1,2,3}.weight        [F]                           */
+  const float* bn_b[3];   /* unetnorm{1,2,3}.bias          [F]                           */
+  const float* bn_mean[3];/* unetnorm{1,2,3}.running_mean  [F]                           */
+  const float* bn_var[3]; /* unetnorm{1,2,3}.running_var   [F]                           */
+} ladine_member_desc;
+
+/*
+ * One batched sampling call: K members x D draws x N images, reverse steps t_first .. t_last.
+ * Replaces the loop at classification_train_separately.py:767-777 (K*D calls of p_sample_loop);
+ * with K = D = 1 it is exactly one p_sample_loop (t_first = T-1, t_last = 0, y_init = NULL),
+ * one p_sample (t_first = t_last = t, y_init = y) or p_sample_t_1to0 (t_first = t_last = 0).
+ */
+typedef struct {
+  uint32_t struct_size;     /* sizeof(ladine_sample_args)                                */
+  int32_t K;                /* members in this call                                      */
+  int32_t N;                /* images                                                    */
+  int32_t D;                /* posterior draws per (member, image)                       */
+  int32_t T;                /* n_steps of the schedule (rows of coef)                    */
+  int32_t t_first;          /* first table index evaluated (T-1 for a full chain)        */
+  int32_t t_last;           /* last table index evaluated (0 for a full chain)           */
+  const float* xf;          /* [K, N, F]  norm(encoder_x(x)) per member (latent_model.py:170-171) */
+  const float* y0hat;       /* [K, N, C]  guidance prediction fed to eps_theta           */
+  const float* ytmean;      /* [K, N, C]  prior mean y_T_mean                            */
+  const float* y_init;      /* [K, D, N, C] or NULL: NULL draws y_T = y_T_mean + z (diffusion_utils.py:139-140) */
+  const float* coef;        /* HOST [T, 8]: inv_q, 1-q, s, gamma0, gamma1, gamma2, sqrt(beta_hat), 0 */
+  const float* noise;       /* [K, D, S, N, C] or NULL.  S = (y_init?0:1) + #steps with t>0; slot order = draw order of the reference */
+  uint64_t seed;            /* Philox4x32-10 key when noise == NULL                      */
+  /* chain identity for the counter-based RNG, so results do not depend on how rows are sharded */
+  const int32_t* member_ids;/* HOST [K] global member index, or NULL for 0..K-1          */
+  int32_t image_offset;     /* global index of image 0 of this call                      */
+  int32_t images_total;     /* global image count (>= image_offset + N); 0 means N       */
+  int32_t draw_offset;      /* global index of draw 0 of this call                       */
+  int32_t draws_total;      /* global draw count; 0 means D                              */
+  float* y_out;             /* [K, D, N, C]  y after step t_last                         */
+  float* traj_out;          /* [K, D, S+1?, N, C] or NULL: every y (y_T first) -- only_last_sample=False */
+  float* prob_out;          /* [K, D, N, C] or NULL: softmax(-(y-1)^2 / temperature) (classification_train_separately.py:392-398) */
+  float temperature;        /* used only when prob_out != NULL                           */
+  void* stream;             /* cudaStream_t                                              */
+} ladine_sample_args;
+
+int ladine_version(void);
+
+/* Bind a handle to CUDA device `device`.  Fails with LADINE_ERR_UNSUPPORTED unless the device
+ * is compute capability 10.x (the kernels are sm_100a-only; there is no fallback path). */
+int ladine_create(int device, ladine_handle** out);
+int ladine_destroy(ladine_handle* h);
+const char* ladine_last_error(const ladine_handle* h);
+
+/* Fold + re-lay-out one member (stream-ordered on `stream`).  The result is owned by the library. */
+int ladine_pack_member(ladine_handle* h, const ladine_member_desc* desc, void* stream, ladine_member** out);
+int ladine_free_member(ladine_handle* h, ladine_member* m);
+/* bytes of device memory held by a packed member; its resolved ladine_precision */
+uint64_t ladine_member_bytes(const ladine_member* m);
+int ladine_member_precision(const ladine_member* m);
+
+/* The hot path.  members: HOST array of K packed members with identical F, C, T, precision. */
+int ladine_sample(ladine_handle* h, const ladine_member* const* members, const ladine_sample_args* args);
+
+/* Write the N(0,1) draws ladine_sample would generate itself for (seed, chain ids) into
+ * noise [K, D, S, N, C], so a Philox run can be replayed through the injected-noise path. */
+int ladine_fill_noise(ladine_handle* h, const ladine_sample_args* args, int32_t num_classes, float* noise);
+
+/* Introspection for benchmarks/tests: kernels launched by the last ladine_sample on this handle,
+ * and current workspace bytes. */
+int64_t ladine_last_launches(const ladine_handle* h);
+uint64_t ladine_workspace_bytes(const ladine_handle* h);
+
+/* Debug/test entry: one trunk GEMM layer (2 or 3) of `member` at table index t on `rows` rows.
+ * h_in  : [rows_pad, Fpad] 16-bit operands in the member's operand type (rows_pad = rows rounded up to 128)
+ * h_out : layer 2 -> [rows_pad, Fpad] 16-bit activations; layer 3 -> unused (may be NULL)
+ * part  : layer 3 -> [rows_pad, Fpad/256, Cpad] FP32 partial lin4 sums; layer 2 -> unused. */
+int ladine_debug_layer(ladine_handle* h, const ladine_member* member, int layer, int t, const void* h_in,
+                       int rows, void* h_out, float* part, void* stream);
+/* padded feature dim and padded class count used by the packed layout */
+int ladine_member_fpad(const ladine_member* m);
+int ladine_member_cpad(const ladine_member* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LADINE_H_ */

@@ -1,0 +1,528 @@
+// C ABI of libladine (include/ladine.h): handle/member lifetime, member packing (fold + re-layout),
+// and the dispatcher of the hot path.  No torch types, no exceptions across the boundary.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "ladine_internal.cuh"
+
+using namespace ladine;
+
+namespace {
+
+int fail(ladine_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+int fail_cuda(ladine_handle* h, cudaError_t e, const char* what) {
+  char buf[256];
+  snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  return fail(h, LADINE_ERR_CUDA, buf);
+}
+
+// ---------------------------------------------------------------------------------------------
+// packing kernels
+// ---------------------------------------------------------------------------------------------
+// A_l[t,f] = E_l[t,f] * s_l[f];  C_l[t,f] = E_l[t,f] * (s_l[f] * b_l[f]) + (beta_l[f] - s_l[f] * mean_l[f])
+// with s = bn.weight / sqrt(bn.running_var + eps)   (SURVEY.md §8a).  `gain` = log2(e) on the tensor path.
+__global__ void fold_tables_kernel(const float* __restrict__ E, const float* __restrict__ lin_b,
+                                   const float* __restrict__ bn_w, const float* __restrict__ bn_b,
+                                   const float* __restrict__ bn_mean, const float* __restrict__ bn_var, float eps,
+                                   float gain, int T, int F, int Fp, float* __restrict__ A, float* __restrict__ Cc) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)T * Fp) return;
+  const int f = (int)(i % Fp);
+  const int t = (int)(i / Fp);
+  float a = 0.f, c = 0.f;
+  if (f < F) {
+    const float s = bn_w[f] / sqrtf(bn_var[f] + eps);
+    const float e = E[(size_t)t * F + f];
+    a = e * s;
+    c = e * (s * lin_b[f]) + (bn_b[f] - s * bn_mean[f]);
+  }
+  A[i] = a * gain;
+  Cc[i] = c * gain;
+}
+
+__global__ void pack_small_kernel(const float* __restrict__ lin1_w, const float* __restrict__ lin4_w,
+                                  const float* __restrict__ lin4_b, int F, int Fp, int C, int Cp, int guidance,
+                                  float* __restrict__ W1y, float* __restrict__ W1g, float* __restrict__ W4,
+                                  float* __restrict__ b4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Fp * Cp) return;
+  const int in1 = guidance ? 2 * C : C;
+  {  // W1y / W1g : [Fp, Cp]
+    const int f = i / Cp, c = i % Cp;
+    float wy = 0.f, wg = 0.f;
+    if (f < F && c < C) {
+      wy = lin1_w[(size_t)f * in1 + c];
+      if (guidance) wg = lin1_w[(size_t)f * in1 + C + c];
+    }
+    W1y[i] = wy;
+    W1g[i] = wg;
+  }
+  {  // W4 : [Cp, Fp]
+    const int c = i / Fp, f = i % Fp;
+    W4[i] = (f < F && c < C) ? lin4_w[(size_t)c * F + f] : 0.f;
+  }
+  if (i < Cp) b4[i] = i < C ? lin4_b[i] : 0.f;
+}
+
+// Wt[k * Fp + n] = W[n * F + k]  (FP32, zero padded) for the SMEM-resident kernel
+__global__ void transpose_pad_kernel(const float* __restrict__ W, int F, int Fp, float* __restrict__ Wt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Fp * Fp) return;
+  const int k = i / Fp, n = i % Fp;
+  Wt[i] = (k < F && n < F) ? W[(size_t)n * F + k] : 0.f;
+}
+
+// W16[n * Fp + k] = round16(W[n * F + k]) (zero padded) for the tensor path ([out][in], K contiguous)
+template <typename T16>
+__global__ void convert_pad_kernel(const float* __restrict__ W, int F, int Fp, T16* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)Fp * Fp) return;
+  const int n = (int)(i / Fp), k = (int)(i % Fp);
+  out[i] = Pack16<T16>::one((n < F && k < F) ? W[(size_t)n * F + k] : 0.f);
+}
+
+// u[k, n, f] = sum_c W1g[f, c] * y_0_hat[k, n, c]   (the step-invariant half of lin1)
+struct GuidanceParams {
+  const float* W1g[LADINE_MAX_GROUP];
+  const float* y0hat;
+  float* u;
+  int N, C, Cp, Fp;
+};
+__global__ void guidance_u_kernel(const __grid_constant__ GuidanceParams p) {
+  const int n = blockIdx.x, k = blockIdx.y;
+  float yh[LADINE_MAX_CLASSES];
+  for (int c = 0; c < p.C; ++c) yh[c] = p.y0hat[((size_t)k * p.N + n) * p.C + c];
+  for (int f = threadIdx.x; f < p.Fp; f += blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < p.C; ++c) acc = fmaf(p.W1g[k][(size_t)f * p.Cp + c], yh[c], acc);
+    p.u[((size_t)k * p.N + n) * p.Fp + f] = acc;
+  }
+}
+
+struct NoiseFillParams {
+  float* noise;
+  uint64_t seed;
+  ChainIds ids;
+  int K, D, S, N, C;
+};
+__global__ void fill_noise_kernel(const __grid_constant__ NoiseFillParams p) {
+  const size_t total = (size_t)p.K * p.D * p.S * p.N * p.C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i;
+    const int c = (int)(r % p.C); r /= p.C;
+    const int n = (int)(r % p.N); r /= p.N;
+    const int s = (int)(r % p.S); r /= p.S;
+    const int d = (int)(r % p.D); r /= p.D;
+    const int k = (int)r;
+    p.noise[i] = philox_normal(p.seed, p.ids.chain(k, d, n), (uint32_t)s, c);
+  }
+}
+
+template <typename T>
+cudaError_t dmalloc(T** p, size_t n, uint64_t* bytes) {
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+  if (e == cudaSuccess) *bytes += n * sizeof(T);
+  return e;
+}
+
+void free_member_buffers(ladine_member* m) {
+  for (int l = 0; l < 3; ++l) {
+    cudaFree(m->A[l]);
+    cudaFree(m->Cc[l]);
+  }
+  cudaFree(m->W1y);
+  cudaFree(m->W1g);
+  cudaFree(m->W4);
+  cudaFree(m->b4);
+  cudaFree(m->W2t);
+  cudaFree(m->W3t);
+  cudaFree(m->W2h);
+  cudaFree(m->W3h);
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+int ensure_workspace(ladine_handle* h, uint64_t bytes) {
+  if (bytes <= h->ws_bytes) return LADINE_OK;
+  if (h->ws) {
+    cudaDeviceSynchronize();  // earlier stream-ordered work may still read the old buffer
+    cudaFree(h->ws);
+    h->ws = nullptr;
+    h->ws_bytes = 0;
+  }
+  cudaError_t e = cudaMalloc(&h->ws, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    char buf[128];
+    snprintf(buf, sizeof buf, "workspace allocation of %llu bytes failed", (unsigned long long)bytes);
+    return fail(h, LADINE_ERR_NOMEM, buf);
+  }
+  h->ws_bytes = bytes;
+  return LADINE_OK;
+}
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+struct SlotInfo {
+  int n_steps, n_slots, n_traj;
+};
+SlotInfo slot_info(const ladine_sample_args& a) {
+  SlotInfo s;
+  s.n_steps = a.t_first - a.t_last + 1;
+  const int noisy = s.n_steps - (a.t_last == 0 ? 1 : 0);  // table index 0 draws no noise
+  s.n_slots = (a.y_init ? 0 : 1) + noisy;
+  s.n_traj = (a.y_init ? 0 : 1) + s.n_steps;
+  return s;
+}
+
+int fill_ids(ladine_handle* h, const ladine_sample_args& a, int k0, int kn, ChainIds* ids) {
+  for (int k = 0; k < kn; ++k) ids->member_gid[k] = a.member_ids ? a.member_ids[k0 + k] : k0 + k;
+  ids->image_offset = a.image_offset;
+  ids->images_total = a.images_total > 0 ? a.images_total : a.N;
+  ids->draw_offset = a.draw_offset;
+  ids->draws_total = a.draws_total > 0 ? a.draws_total : a.D;
+  if (ids->image_offset < 0 || ids->draw_offset < 0 || ids->image_offset + a.N > ids->images_total ||
+      ids->draw_offset + a.D > ids->draws_total)
+    return fail(h, LADINE_ERR_INVALID, "image/draw offsets exceed images_total/draws_total");
+  return LADINE_OK;
+}
+
+}  // namespace
+
+namespace ladine {
+cudaError_t launch_guidance_u(const ladine_member* const* members, int K, int N, const float* y0hat, float* u,
+                              cudaStream_t st) {
+  GuidanceParams p{};
+  for (int k = 0; k < K; ++k) p.W1g[k] = members[k]->W1g;
+  p.y0hat = y0hat;
+  p.u = u;
+  p.N = N;
+  p.C = members[0]->C;
+  p.Cp = members[0]->Cp;
+  p.Fp = members[0]->Fp;
+  guidance_u_kernel<<<dim3(N, K), 256, 0, st>>>(p);
+  return cudaGetLastError();
+}
+}  // namespace ladine
+
+// =============================================================================================
+extern "C" {
+
+int ladine_version(void) { return LADINE_ABI_VERSION; }
+
+int ladine_create(int device, ladine_handle** out) {
+  if (!out) return LADINE_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    cudaGetLastError();
+    return LADINE_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LADINE_ERR_CUDA;
+  if (prop.major != 10) return LADINE_ERR_UNSUPPORTED;  // sm_100a kernels only; no fallback
+  ladine_handle* h = new (std::nothrow) ladine_handle();
+  if (!h) return LADINE_ERR_NOMEM;
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  *out = h;
+  return LADINE_OK;
+}
+
+int ladine_destroy(ladine_handle* h) {
+  if (!h) return LADINE_ERR_INVALID;
+  {
+    DeviceGuard g(h->device);
+    if (h->ws) {
+      cudaDeviceSynchronize();
+      cudaFree(h->ws);
+    }
+  }
+  delete h;
+  return LADINE_OK;
+}
+
+const char* ladine_last_error(const ladine_handle* h) { return h ? h->err.c_str() : "null handle"; }
+int64_t ladine_last_launches(const ladine_handle* h) { return h ? h->last_launches : 0; }
+uint64_t ladine_workspace_bytes(const ladine_handle* h) { return h ? h->ws_bytes : 0; }
+uint64_t ladine_member_bytes(const ladine_member* m) { return m ? m->bytes : 0; }
+int ladine_member_precision(const ladine_member* m) { return m ? m->precision : LADINE_ERR_INVALID; }
+int ladine_member_fpad(const ladine_member* m) { return m ? m->Fp : LADINE_ERR_INVALID; }
+int ladine_member_cpad(const ladine_member* m) { return m ? m->Cp : LADINE_ERR_INVALID; }
+
+int ladine_pack_member(ladine_handle* h, const ladine_member_desc* d, void* stream, ladine_member** out) {
+  if (!h) return LADINE_ERR_INVALID;
+  if (!d || !out) return fail(h, LADINE_ERR_INVALID, "null descriptor or output");
+  *out = nullptr;
+  if (d->struct_size != sizeof(ladine_member_desc)) return fail(h, LADINE_ERR_INVALID, "ladine_member_desc size mismatch");
+  if (d->feature_dim < 1 || d->num_classes < 1 || d->n_steps < 1 || d->emb_rows < d->n_steps)
+    return fail(h, LADINE_ERR_INVALID, "feature_dim, num_classes, n_steps must be >= 1 and emb_rows >= n_steps");
+  if (d->num_classes > LADINE_MAX_CLASSES)
+    return fail(h, LADINE_ERR_UNSUPPORTED, "num_classes > 16 is not supported by the fused kernels");
+  const void* ptrs[] = {d->lin1_w, d->lin1_b, d->lin2_w, d->lin2_b, d->lin3_w, d->lin3_b, d->lin4_w, d->lin4_b,
+                        d->emb[0], d->emb[1], d->emb[2], d->bn_w[0], d->bn_w[1], d->bn_w[2], d->bn_b[0], d->bn_b[1],
+                        d->bn_b[2], d->bn_mean[0], d->bn_mean[1], d->bn_mean[2], d->bn_var[0], d->bn_var[1], d->bn_var[2]};
+  for (const void* p : ptrs)
+    if (!p) return fail(h, LADINE_ERR_INVALID, "null parameter pointer in ladine_member_desc");
+
+  int prec = d->precision;
+  if (prec == LADINE_PREC_AUTO) prec = d->feature_dim <= 128 ? LADINE_PREC_FP32 : LADINE_PREC_FP16;
+  if (prec == LADINE_PREC_FP32 && d->feature_dim > 128)
+    return fail(h, LADINE_ERR_UNSUPPORTED,
+                "FP32 SMEM-resident path needs feature_dim <= 128 (two FP32 square layers must fit in shared memory)");
+  if (prec != LADINE_PREC_FP32 && prec != LADINE_PREC_FP16 && prec != LADINE_PREC_BF16)
+    return fail(h, LADINE_ERR_INVALID, "unknown precision");
+
+  DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ladine_member* m = new (std::nothrow) ladine_member();
+  if (!m) return fail(h, LADINE_ERR_NOMEM, "host allocation failed");
+  m->F = d->feature_dim;
+  m->C = d->num_classes;
+  m->Cp = cpad_of(m->C);
+  m->T = d->n_steps;
+  m->guidance = d->guidance ? 1 : 0;
+  m->precision = prec;
+  m->device = h->device;
+  const bool tensor = prec != LADINE_PREC_FP32;
+  m->Fp = tensor ? (int)align_up(m->F, 256) : (int)align_up(m->F, 32);
+  const int F = m->F, Fp = m->Fp, T = m->T, Cp = m->Cp;
+
+  cudaError_t e = cudaSuccess;
+  auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
+  for (int l = 0; l < 3 && e == cudaSuccess; ++l) {
+    ok(dmalloc(&m->A[l], (size_t)T * Fp, &m->bytes));
+    ok(dmalloc(&m->Cc[l], (size_t)T * Fp, &m->bytes));
+  }
+  ok(dmalloc(&m->W1y, (size_t)Fp * Cp, &m->bytes));
+  ok(dmalloc(&m->W1g, (size_t)Fp * Cp, &m->bytes));
+  ok(dmalloc(&m->W4, (size_t)Cp * Fp, &m->bytes));
+  ok(dmalloc(&m->b4, (size_t)Cp, &m->bytes));
+  if (tensor) {
+    ok(dmalloc(reinterpret_cast<uint16_t**>(&m->W2h), (size_t)Fp * Fp, &m->bytes));
+    ok(dmalloc(reinterpret_cast<uint16_t**>(&m->W3h), (size_t)Fp * Fp, &m->bytes));
+  } else {
+    ok(dmalloc(&m->W2t, (size_t)Fp * Fp, &m->bytes));
+    ok(dmalloc(&m->W3t, (size_t)Fp * Fp, &m->bytes));
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    free_member_buffers(m);
+    delete m;
+    return fail(h, LADINE_ERR_NOMEM, "device allocation failed while packing a member");
+  }
+
+  const float gain = tensor ? kLog2e : 1.0f;
+  const float* lin_b[3] = {d->lin1_b, d->lin2_b, d->lin3_b};
+  const size_t tf = (size_t)T * Fp;
+  for (int l = 0; l < 3; ++l) {
+    fold_tables_kernel<<<(unsigned)((tf + 255) / 256), 256, 0, st>>>(d->emb[l], lin_b[l], d->bn_w[l], d->bn_b[l],
+                                                                     d->bn_mean[l], d->bn_var[l], d->bn_eps, gain, T, F,
+                                                                     Fp, m->A[l], m->Cc[l]);
+  }
+  pack_small_kernel<<<(Fp * Cp + 255) / 256, 256, 0, st>>>(d->lin1_w, d->lin4_w, d->lin4_b, F, Fp, m->C, Cp, m->guidance,
+                                                           m->W1y, m->W1g, m->W4, m->b4);
+  const size_t ff = (size_t)Fp * Fp;
+  const unsigned gff = (unsigned)((ff + 255) / 256);
+  if (!tensor) {
+    transpose_pad_kernel<<<gff, 256, 0, st>>>(d->lin2_w, F, Fp, m->W2t);
+    transpose_pad_kernel<<<gff, 256, 0, st>>>(d->lin3_w, F, Fp, m->W3t);
+  } else if (prec == LADINE_PREC_FP16) {
+    convert_pad_kernel<__half><<<gff, 256, 0, st>>>(d->lin2_w, F, Fp, static_cast<__half*>(m->W2h));
+    convert_pad_kernel<__half><<<gff, 256, 0, st>>>(d->lin3_w, F, Fp, static_cast<__half*>(m->W3h));
+  } else {
+    convert_pad_kernel<__nv_bfloat16><<<gff, 256, 0, st>>>(d->lin2_w, F, Fp, static_cast<__nv_bfloat16*>(m->W2h));
+    convert_pad_kernel<__nv_bfloat16><<<gff, 256, 0, st>>>(d->lin3_w, F, Fp, static_cast<__nv_bfloat16*>(m->W3h));
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    free_member_buffers(m);
+    delete m;
+    return fail_cuda(h, e, "member packing kernels");
+  }
+  *out = m;
+  return LADINE_OK;
+}
+
+int ladine_free_member(ladine_handle* h, ladine_member* m) {
+  if (!m) return LADINE_ERR_INVALID;
+  DeviceGuard guard(m->device);
+  cudaDeviceSynchronize();
+  free_member_buffers(m);
+  delete m;
+  (void)h;
+  return LADINE_OK;
+}
+
+static int validate_sample(ladine_handle* h, const ladine_member* const* members, const ladine_sample_args* a) {
+  if (!members || !a) return fail(h, LADINE_ERR_INVALID, "null members or args");
+  if (a->struct_size != sizeof(ladine_sample_args)) return fail(h, LADINE_ERR_INVALID, "ladine_sample_args size mismatch");
+  if (a->K < 1 || a->N < 1 || a->D < 1 || a->T < 1) return fail(h, LADINE_ERR_INVALID, "K, N, D, T must be >= 1");
+  if (a->t_first < a->t_last || a->t_last < 0 || a->t_first >= a->T)
+    return fail(h, LADINE_ERR_INVALID, "need 0 <= t_last <= t_first < T");
+  if (!a->xf || !a->y0hat || !a->ytmean || !a->coef || !a->y_out)
+    return fail(h, LADINE_ERR_INVALID, "xf, y0hat, ytmean, coef and y_out are required");
+  if (a->prob_out && !(a->temperature > 0.f)) return fail(h, LADINE_ERR_INVALID, "temperature must be > 0");
+  const ladine_member* m0 = members[0];
+  for (int k = 0; k < a->K; ++k) {
+    const ladine_member* m = members[k];
+    if (!m) return fail(h, LADINE_ERR_INVALID, "null member");
+    if (m->device != h->device) return fail(h, LADINE_ERR_INVALID, "member packed on another device");
+    if (m->F != m0->F || m->C != m0->C || m->precision != m0->precision || m->guidance != m0->guidance)
+      return fail(h, LADINE_ERR_INVALID, "members of one call must share feature_dim, num_classes, guidance and precision");
+    if (m->T < a->T) return fail(h, LADINE_ERR_INVALID, "member packed with fewer table rows than args.T");
+  }
+  return LADINE_OK;
+}
+
+int ladine_sample(ladine_handle* h, const ladine_member* const* members, const ladine_sample_args* a) {
+  if (!h) return LADINE_ERR_INVALID;
+  int rc = validate_sample(h, members, a);
+  if (rc != LADINE_OK) return rc;
+  DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  const ladine_member* m0 = members[0];
+  const int F = m0->F, Fp = m0->Fp, C = m0->C, Cp = m0->Cp;
+  const SlotInfo si = slot_info(*a);
+  const bool tensor = m0->precision != LADINE_PREC_FP32;
+  h->last_launches = 0;
+
+  const StepCoef* h_coef = reinterpret_cast<const StepCoef*>(a->coef);
+  static_assert(sizeof(StepCoef) == 8 * sizeof(float), "coef rows are 8 floats");
+
+  // workspace: sized for one launch group
+  const int G = a->K < LADINE_MAX_GROUP ? a->K : LADINE_MAX_GROUP;
+  const int rows = a->N * a->D;
+  const int rows_pad = (rows + 127) / 128 * 128;
+  const uint64_t m_total = (uint64_t)G * rows_pad;
+  uint64_t off = 0;
+  const uint64_t o_coef = off; off = align_up(off + (uint64_t)a->T * sizeof(StepCoef), 1024);
+  const uint64_t o_u = off; off = align_up(off + (uint64_t)G * a->N * Fp * 4, 1024);
+  uint64_t o_h1 = 0, o_h2 = 0, o_part = 0, o_y = 0;
+  if (tensor) {
+    o_h1 = off; off = align_up(off + m_total * Fp * 2, 1024);
+    o_h2 = off; off = align_up(off + m_total * Fp * 2, 1024);
+    o_part = off; off = align_up(off + m_total * (Fp / 256) * Cp * 4, 1024);
+    o_y = off; off = align_up(off + m_total * Cp * 4, 1024);
+  }
+  rc = ensure_workspace(h, off);
+  if (rc != LADINE_OK) return rc;
+  uint8_t* ws = static_cast<uint8_t*>(h->ws);
+  cudaError_t e;
+
+  if (!tensor) {
+    const size_t smem = resident_smem_bytes(Fp, Cp);
+    if ((int)smem > h->max_smem_optin) return fail(h, LADINE_ERR_UNSUPPORTED, "shared memory budget exceeded");
+    e = cudaMemcpyAsync(ws + o_coef, a->coef, (size_t)a->T * sizeof(StepCoef), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail_cuda(h, e, "coefficient upload");
+  }
+
+  for (int k0 = 0; k0 < a->K; k0 += LADINE_MAX_GROUP) {
+    const int kn = (a->K - k0) < LADINE_MAX_GROUP ? (a->K - k0) : LADINE_MAX_GROUP;
+    ladine_sample_args g = *a;
+    g.K = kn;
+    g.xf = a->xf + (size_t)k0 * a->N * F;
+    g.y0hat = a->y0hat + (size_t)k0 * a->N * C;
+    g.ytmean = a->ytmean + (size_t)k0 * a->N * C;
+    const size_t kdnc = (size_t)a->D * a->N * C;
+    if (a->y_init) g.y_init = a->y_init + k0 * kdnc;
+    if (a->noise) g.noise = a->noise + k0 * kdnc * si.n_slots;
+    g.y_out = a->y_out + k0 * kdnc;
+    if (a->traj_out) g.traj_out = a->traj_out + k0 * kdnc * si.n_traj;
+    if (a->prob_out) g.prob_out = a->prob_out + k0 * kdnc;
+    ChainIds ids{};
+    rc = fill_ids(h, *a, k0, kn, &ids);
+    if (rc != LADINE_OK) return rc;
+
+    float* d_u = reinterpret_cast<float*>(ws + o_u);
+    e = launch_guidance_u(members + k0, kn, a->N, g.y0hat, d_u, st);
+    if (e != cudaSuccess) return fail_cuda(h, e, "guidance projection kernel");
+    h->last_launches += 1;
+
+    if (!tensor) {
+      e = launch_resident(h, members + k0, g, ids, reinterpret_cast<const StepCoef*>(ws + o_coef), d_u, si.n_slots,
+                          si.n_traj, st, &h->last_launches);
+      if (e != cudaSuccess) return fail_cuda(h, e, "resident sampler launch");
+    } else {
+      TensorWorkspace tw;
+      tw.h1 = ws + o_h1;
+      tw.h2 = ws + o_h2;
+      tw.part = reinterpret_cast<float*>(ws + o_part);
+      tw.ybuf = reinterpret_cast<float*>(ws + o_y);
+      tw.u = d_u;
+      std::string err;
+      e = launch_tensor_chain(h, members + k0, g, ids, h_coef, tw, si.n_slots, si.n_traj, st, &h->last_launches, &err);
+      if (e != cudaSuccess) {
+        if (!err.empty()) return fail(h, LADINE_ERR_CUDA, err);
+        return fail_cuda(h, e, "tensor-core sampler launch");
+      }
+    }
+  }
+  return LADINE_OK;
+}
+
+int ladine_fill_noise(ladine_handle* h, const ladine_sample_args* a, int32_t num_classes, float* noise) {
+  if (!h) return LADINE_ERR_INVALID;
+  if (!a || !noise || num_classes < 1) return fail(h, LADINE_ERR_INVALID, "null args or output");
+  if (a->K < 1 || a->K > LADINE_MAX_GROUP * 64 || a->N < 1 || a->D < 1 || a->t_first < a->t_last || a->t_last < 0)
+    return fail(h, LADINE_ERR_INVALID, "bad K/N/D/t range");
+  DeviceGuard guard(h->device);
+  const SlotInfo si = slot_info(*a);
+  const size_t kdsnc = (size_t)a->D * si.n_slots * a->N * num_classes;
+  for (int k0 = 0; k0 < a->K; k0 += LADINE_MAX_GROUP) {
+    const int kn = (a->K - k0) < LADINE_MAX_GROUP ? (a->K - k0) : LADINE_MAX_GROUP;
+    NoiseFillParams p{};
+    int rc = fill_ids(h, *a, k0, kn, &p.ids);
+    if (rc != LADINE_OK) return rc;
+    p.noise = noise + k0 * kdsnc;
+    p.seed = a->seed;
+    p.K = kn;
+    p.D = a->D;
+    p.S = si.n_slots;
+    p.N = a->N;
+    p.C = num_classes;
+    const size_t total = kn * kdsnc;
+    if (total == 0) continue;
+    const unsigned grid = (unsigned)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    fill_noise_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(a->stream)>>>(p);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(h, e, "noise fill kernel");
+  return LADINE_OK;
+}
+
+int ladine_debug_layer(ladine_handle* h, const ladine_member* member, int layer, int t, const void* h_in, int rows,
+                       void* h_out, float* part, void* stream) {
+  if (!h) return LADINE_ERR_INVALID;
+  if (!member || !h_in || rows < 1 || (layer != 2 && layer != 3) || t < 0 || t >= member->T)
+    return fail(h, LADINE_ERR_INVALID, "bad debug-layer arguments");
+  if (member->precision == LADINE_PREC_FP32) return fail(h, LADINE_ERR_UNSUPPORTED, "debug layer is for the tensor path");
+  if ((layer == 2 && !h_out) || (layer == 3 && !part)) return fail(h, LADINE_ERR_INVALID, "missing output buffer");
+  DeviceGuard guard(h->device);
+  std::string err;
+  cudaError_t e = launch_debug_layer(h, member, layer, t, h_in, rows, h_out, part, static_cast<cudaStream_t>(stream), &err);
+  if (e != cudaSuccess) {
+    if (!err.empty()) return fail(h, LADINE_ERR_CUDA, err);
+    return fail_cuda(h, e, "debug layer launch");
+  }
+  return LADINE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// Host-side structures shared by the translation units of libladine.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "ladine_common.cuh"
+
+struct ladine_member {
+  int F = 0;        // feature_dim as given
+  int Fp = 0;       // padded feature dim (multiple of 32 for FP32-resident, 256 for tensor path)
+  int C = 0;        // num_classes
+  int Cp = 0;       // padded class count {2,4,8,16}
+  int T = 0;        // usable table rows
+  int guidance = 0;
+  int precision = 0;  // resolved ladine_precision (never AUTO)
+  int device = 0;
+  // FP32 per-step scale/shift rows, [T, Fp] each.  Tensor path: pre-multiplied by log2(e).
+  float* A[3] = {nullptr, nullptr, nullptr};
+  float* Cc[3] = {nullptr, nullptr, nullptr};
+  float* W1y = nullptr;  // [Fp, Cp]  lin1 weight columns that multiply y_t
+  float* W1g = nullptr;  // [Fp, Cp]  lin1 weight columns that multiply y_0_hat (zeros without guidance)
+  float* W4 = nullptr;   // [Cp, Fp]
+  float* b4 = nullptr;   // [Cp]
+  // FP32-resident path: k-major (transposed) FP32 weights  Wt[k * Fp + n] = W[n][k]
+  float* W2t = nullptr;
+  float* W3t = nullptr;
+  // tensor path: 16-bit [Fp, Fp] row-major ([out][in], K contiguous)
+  void* W2h = nullptr;
+  void* W3h = nullptr;
+  uint64_t bytes = 0;
+};
+
+struct ladine_handle {
+  int device = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  std::string err;
+  int64_t last_launches = 0;
+  // grow-only workspace
+  void* ws = nullptr;
+  uint64_t ws_bytes = 0;
+  // driver entry point for tensor-map encoding (resolved lazily through the runtime)
+  void* encode_tiled = nullptr;
+};
+
+namespace ladine {
+
+inline int cpad_of(int C) { return C <= 2 ? 2 : C <= 4 ? 4 : C <= 8 ? 8 : 16; }
+
+struct RowGeom {
+  int K, N, D;
+  int rows;      // N * D valid rows per member
+  int rows_pad;  // rounded up to the row-tile size
+};
+
+// ---- FP32 SMEM-resident path (ladine_resident.cu) ----
+cudaError_t launch_resident(const ladine_handle* h, const ladine_member* const* members, const ladine_sample_args& a,
+                            const ChainIds& ids, const StepCoef* d_coef, float* d_u, int n_slots, int n_traj,
+                            cudaStream_t st, int64_t* launches);
+size_t resident_smem_bytes(int Fp, int Cp);
+
+// ---- tensor-core path (ladine_tensor.cu) ----
+struct TensorWorkspace {
+  void* h1;      // [K * rows_pad, Fp] 16-bit
+  void* h2;      // [K * rows_pad, Fp] 16-bit
+  float* part;   // [K * rows_pad, Fp / 256, Cp]
+  float* ybuf;   // [K * rows_pad, Cp]
+  float* u;      // [K, N, Fp]
+};
+cudaError_t launch_tensor_chain(ladine_handle* h, const ladine_member* const* members, const ladine_sample_args& a,
+                                const ChainIds& ids, const StepCoef* h_coef, const TensorWorkspace& ws,
+                                int n_slots, int n_traj, cudaStream_t st, int64_t* launches, std::string* err);
+cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int layer, int t, const void* h_in, int rows,
+                               void* h_out, float* part, cudaStream_t st, std::string* err);
+size_t tensor_gemm_smem_bytes(int Cp);
+
+// ---- shared small kernels (ladine_api.cu) ----
+cudaError_t launch_guidance_u(const ladine_member* const* members, int K, int N, const float* y0hat, float* u,
+                              cudaStream_t st);
+
+}  // namespace ladine

@@ -1,0 +1,748 @@
+// Tensor-core path of the LaDiNE sampler for the shipped shape (feature_dim = 4096): the two square
+// ConditionalLinear layers of every reverse step run on tcgen05 (UTCHMMA) with FP32 accumulators in
+// TMEM, operands staged by TMA, and everything around them fused into the epilogues.
+//
+// Per reverse step t (diffusion_utils.py:54-92 / :96-111 around latent_model.py:172-184), for ALL
+// members x draws x images at once:
+//   gemm<2>   h2 = softplus(A2_t * (h1 W2^T) + C2_t)                       -> 16-bit [rows, F]
+//   gemm<3>   h3 = softplus(A3_t * (h2 W3^T) + C3_t); part = h3 . W4^T     -> FP32 [rows, F/256, Cp]
+//   tailhead  eps = sum(part) + b4; y_{t-1} = posterior(y_t, eps, z);     (FP32, reference op order)
+//             h1 = softplus(A1_{t-1} * (W1y y_{t-1} + u) + C1_{t-1}) * xf  -> 16-bit [rows, F]
+// where A_l/C_l fold gamma_l[t], the Linear bias and the eval-mode BatchNorm.
+//
+// GEMM kernel: persistent, warp-specialised, one CTA per SM.
+//   warp 0      TMA producer   (cp.async.bulk.tensor 2D, 128B swizzle, 4-stage mbarrier ring)
+//   warp 1      MMA issuer     (tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16, one thread)
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b, scale/shift + softplus in the log2 domain, store)
+//   TMEM: 2 accumulator stages x 256 columns so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cstdio>
+
+#include "ladine_internal.cuh"
+
+namespace ladine {
+namespace {
+
+constexpr int BM = 128;   // rows per tile  (UMMA M)
+constexpr int BN = 256;   // cols per tile  (UMMA N)
+constexpr int BK = 64;    // K per stage    (64 x 2 B = one 128-byte swizzle row)
+constexpr int UK = 16;    // K per tcgen05.mma (kind::f16)
+constexpr int kStages = 4;
+constexpr int kABytes = BM * BK * 2;
+constexpr int kBBytes = BN * BK * 2;
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = kAccStages * BN;  // 512
+constexpr int kGemmThreads = 192;
+constexpr int kEpiThreads = 128;
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+      printf("ladine: mbarrier timeout role=%d block=%d thread=%d bar=%u parity=%u\n", who, (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major; issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every tcgen05 op issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory operand descriptor (PTX ISA "tcgen05 shared memory
+// descriptor"): start address >> 4 in bits [0,14); leading byte offset (unused for swizzled K-major,
+// encoded 1) in [16,30); stride byte offset = 8 rows x 128 B = 1024 B (>>4 = 64) in [32,46);
+// descriptor version 1 in [46,48); layout type 2 = SWIZZLE_128B in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMM + fused epilogue
+// ------------------------------------------------------------------------------------------
+struct GemmParams {
+  CUtensorMap tmA;                     // activations in  [M_total, Fp] 16-bit, box 64 x 128
+  CUtensorMap tmB[LADINE_MAX_GROUP];   // member weights  [Fp, Fp]      16-bit, box 64 x 256
+  const float* scale[LADINE_MAX_GROUP];  // A_l[t] row of each member (already offset to row t), x log2e
+  const float* shift[LADINE_MAX_GROUP];  // C_l[t] row, x log2e
+  const float* W4[LADINE_MAX_GROUP];     // [Cp, Fp]  (layer 3 only)
+  void* h_out;                         // layer 2: [M_total, Fp] 16-bit
+  float* part;                         // layer 3: [M_total, NB, Cp]
+  int Fp, NB, KB;                      // padded feature dim, N tiles (Fp/256), K blocks (Fp/64)
+  int mblk;                            // row tiles per member
+  int rows;                            // valid rows per member
+  int rows_pad;                        // mblk * 128
+  int num_tiles;                       // K * mblk * NB
+  uint32_t idesc;
+};
+
+struct __align__(8) GemmBarriers {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t acc_full[kAccStages];
+  uint64_t acc_empty[kAccStages];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+
+template <int LAYER, typename T16, int CP>
+__global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                               // kStages x 16 KiB
+  uint8_t* sB = smem + kStages * kABytes;           // kStages x 32 KiB
+  float* sEpi = reinterpret_cast<float*>(smem + kStages * kStageBytes);  // scale[256] shift[256] (W4[CP][256])
+  GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(sEpi + (LAYER == 3 ? BN * (2 + CP) : 2 * BN));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&bars->full[s]), 1);
+      mbar_init(smem_u32(&bars->empty[s]), 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(smem_u32(&bars->acc_full[s]), 1);
+      mbar_init(smem_u32(&bars->acc_empty[s]), kEpiThreads / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&p.tmA);
+  }
+  if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  const int tiles_per_member = p.mblk * p.NB;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int member = tile / tiles_per_member;
+        const int rem = tile - member * tiles_per_member;
+        const int nb = rem / p.mblk, mb = rem - nb * p.mblk;
+        const int arow = member * p.rows_pad + mb * BM;
+        const CUtensorMap* tb = &p.tmB[member];
+        for (int kb = 0; kb < p.KB; ++kb) {
+          mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u, 0);
+          const uint32_t fb = smem_u32(&bars->full[stage]);
+          mbar_arrive_expect_tx(fb, kStageBytes);
+          tma_load_2d(smem_u32(sA + stage * kABytes), &p.tmA, fb, kb * BK, arow);
+          tma_load_2d(smem_u32(sB + stage * kBBytes), tb, fb, kb * BK, nb * BN);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(smem_u32(&bars->acc_empty[as]), aphase ^ 1u, 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < p.KB; ++kb) {
+          mbar_wait(smem_u32(&bars->full[stage]), phase, 2);
+          tc_fence_after();
+          const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * kABytes));
+          const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * kBBytes));
+#pragma unroll
+          for (int k4 = 0; k4 < BK / UK; ++k4) {
+            // +32 bytes per K=16 slice inside the 128-byte swizzle row: +2 in the >>4 address field
+            umma_f16(d_tmem, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), p.idesc, (uint32_t)((kb | k4) != 0));
+          }
+          umma_commit(smem_u32(&bars->empty[stage]));  // frees the smem slot when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(smem_u32(&bars->acc_full[as]));  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int et = threadIdx.x - 64;         // 0..127
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;
+    float* sScale = sEpi;
+    float* sShift = sEpi + BN;
+    float* sW4 = sEpi + 2 * BN;              // [CP][BN]
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int member = tile / tiles_per_member;
+      const int rem = tile - member * tiles_per_member;
+      const int nb = rem / p.mblk, mb = rem - nb * p.mblk;
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      // stage this tile's per-column parameters (independent of the accumulator: issued before the wait)
+      {
+        const float* gs = p.scale[member] + nb * BN;
+        const float* gh = p.shift[member] + nb * BN;
+        const float s0 = __ldg(gs + et), s1 = __ldg(gs + et + 128);
+        const float h0 = __ldg(gh + et), h1 = __ldg(gh + et + 128);
+        float w4v[LAYER == 3 ? 2 * CP : 1];
+        if (LAYER == 3) {
+#pragma unroll
+          for (int c = 0; c < CP; ++c) {
+            w4v[2 * c] = __ldg(p.W4[member] + (size_t)c * p.Fp + nb * BN + et);
+            w4v[2 * c + 1] = __ldg(p.W4[member] + (size_t)c * p.Fp + nb * BN + et + 128);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
+        sScale[et] = s0; sScale[et + 128] = s1;
+        sShift[et] = h0; sShift[et + 128] = h1;
+        if (LAYER == 3) {
+#pragma unroll
+          for (int c = 0; c < CP; ++c) {
+            sW4[c * BN + et] = w4v[2 * c];
+            sW4[c * BN + et + 128] = w4v[2 * c + 1];
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(smem_u32(&bars->acc_full[as]), aphase, 3);
+      tc_fence_after();
+
+      const int row_m = mb * BM + row_in_tile;          // row within the member
+      const bool valid = row_m < p.rows;
+      const size_t grow = (size_t)member * p.rows_pad + row_m;
+      const uint32_t taddr = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quad * 32) << 16);
+      float eacc[LAYER == 3 ? CP : 1];
+#pragma unroll
+      for (int c = 0; c < (LAYER == 3 ? CP : 1); ++c) eacc[c] = 0.f;
+
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(ch * 32), v);
+        tmem_ld_wait();
+        float hcol[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 sc = *reinterpret_cast<const float4*>(sScale + ch * 32 + j4 * 4);
+          const float4 sh = *reinterpret_cast<const float4*>(sShift + ch * 32 + j4 * 4);
+          hcol[4 * j4 + 0] = softplus_log2dom(fmaf(sc.x, __uint_as_float(v[4 * j4 + 0]), sh.x));
+          hcol[4 * j4 + 1] = softplus_log2dom(fmaf(sc.y, __uint_as_float(v[4 * j4 + 1]), sh.y));
+          hcol[4 * j4 + 2] = softplus_log2dom(fmaf(sc.z, __uint_as_float(v[4 * j4 + 2]), sh.z));
+          hcol[4 * j4 + 3] = softplus_log2dom(fmaf(sc.w, __uint_as_float(v[4 * j4 + 3]), sh.w));
+        }
+        if (LAYER == 2) {
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<T16*>(p.h_out) + grow * p.Fp + nb * BN + ch * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = Pack16<T16>::pack(hcol[8 * q + 0], hcol[8 * q + 1]);
+              o.y = Pack16<T16>::pack(hcol[8 * q + 2], hcol[8 * q + 3]);
+              o.z = Pack16<T16>::pack(hcol[8 * q + 4], hcol[8 * q + 5]);
+              o.w = Pack16<T16>::pack(hcol[8 * q + 6], hcol[8 * q + 7]);
+              dst[q] = o;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < CP; ++c) {
+            float e = eacc[c];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 w = *reinterpret_cast<const float4*>(sW4 + c * BN + ch * 32 + j4 * 4);
+              e = fmaf(hcol[4 * j4 + 0], w.x, e);
+              e = fmaf(hcol[4 * j4 + 1], w.y, e);
+              e = fmaf(hcol[4 * j4 + 2], w.z, e);
+              e = fmaf(hcol[4 * j4 + 3], w.w, e);
+            }
+            eacc[c] = e;
+          }
+        }
+      }
+      // accumulator stage drained: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[as]));
+      if (LAYER == 3 && valid) {
+        float* dst = p.part + (grow * p.NB + nb) * CP;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) dst[c] = eacc[c];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// tail (posterior update of step t) + head (lin1 of step t-1)
+// ------------------------------------------------------------------------------------------
+enum TailMode { kInit = 0, kMid = 1, kFinal = 2 };
+
+struct TailHeadParams {
+  const float* A1[LADINE_MAX_GROUP];   // row of the NEXT step (t-1), x log2e
+  const float* C1[LADINE_MAX_GROUP];
+  const float* W1y[LADINE_MAX_GROUP];  // [Fp, Cp]
+  const float* b4[LADINE_MAX_GROUP];
+  const float* part;   // [M_total, NB, Cp]
+  float* ybuf;         // [M_total, Cp]  chain state
+  const float* xf;     // [K, N, Fin]
+  const float* u;      // [K, N, Fp]
+  const float* ytmean; // [K, N, C]
+  const float* y_init; // [K, D, N, C] or null (kInit only)
+  const float* noise;  // [K, D, S, N, C] or null
+  void* h1;            // [M_total, Fp] 16-bit
+  float* y_out;        // kFinal / last step
+  float* traj_out;
+  float* prob_out;
+  float temperature;
+  StepCoef coef;       // coefficients of the step being finished (unused for kInit)
+  uint64_t seed;
+  ChainIds ids;
+  int t;               // table index of the step being finished (kInit: unused)
+  int slot;            // noise slot / trajectory entry consumed-written by this launch
+  int traj_entry;
+  int N, D, C, Fin, Fp, NB, rows_pad, n_slots, n_traj, dchunk, write_out;
+};
+
+constexpr int kTailThreads = 256;
+constexpr int kTailMaxRows = 32;  // draws handled per CTA
+
+template <int MODE, typename T16, int CP>
+__global__ void __launch_bounds__(kTailThreads) tailhead_kernel(const __grid_constant__ TailHeadParams p) {
+  __shared__ float sY[kTailMaxRows * CP];
+  const int n = blockIdx.x, k = blockIdx.y;
+  const int d0 = blockIdx.z * p.dchunk;
+  const int nd = min(p.dchunk, p.D - d0);
+  const int tid = threadIdx.x;
+  const int C = p.C;
+
+  // ---------------- tail: finish step t for rows (k, n, d0..d0+nd) ----------------
+  for (int i = tid; i < nd * C; i += kTailThreads) {
+    const int dl = i / C, c = i - dl * C;
+    const int d = d0 + dl;
+    const size_t grow = (size_t)k * p.rows_pad + (size_t)n * p.D + d;
+    const float mu = __ldg(p.ytmean + ((size_t)k * p.N + n) * C + c);
+    float yn;
+    if (MODE == kInit) {
+      if (p.y_init) {
+        yn = __ldg(p.y_init + (((size_t)k * p.D + d) * p.N + n) * C + c);
+      } else {
+        const float z = p.noise ? __ldg(p.noise + ((((size_t)k * p.D + d) * p.n_slots + 0) * p.N + n) * C + c)
+                                : philox_normal(p.seed, p.ids.chain(k, d, n), 0u, c);
+        yn = __fadd_rn(z, mu);
+      }
+    } else {
+      float eps = __ldg(p.b4[k] + c);
+      const float* pp = p.part + (grow * p.NB) * CP + c;
+      for (int nb = 0; nb < p.NB; ++nb) eps += pp[nb * CP];  // fixed order: deterministic
+      const float y = p.ybuf[grow * CP + c];
+      if (p.t > 0) {
+        const float z = p.noise ? __ldg(p.noise + ((((size_t)k * p.D + d) * p.n_slots + p.slot) * p.N + n) * C + c)
+                                : philox_normal(p.seed, p.ids.chain(k, d, n), (uint32_t)p.slot, c);
+        yn = posterior_step_op(p.coef, y, mu, eps, z);
+      } else {
+        yn = y0_reparam_op(p.coef, y, mu, eps);
+      }
+    }
+    p.ybuf[grow * CP + c] = yn;
+    sY[dl * CP + c] = yn;
+    if (p.traj_out && p.traj_entry >= 0)
+      p.traj_out[((((size_t)k * p.D + d) * p.n_traj + p.traj_entry) * p.N + n) * C + c] = yn;
+    if (p.write_out) p.y_out[(((size_t)k * p.D + d) * p.N + n) * C + c] = yn;
+  }
+  if (MODE == kFinal && !p.write_out) return;
+  __syncthreads();
+  if (p.write_out && p.prob_out) {
+    // softmax(-(y-1)^2 / temperature) -- classification_train_separately.py:392-398
+    for (int dl = tid; dl < nd; dl += kTailThreads) {
+      float mx = -INFINITY;
+      for (int c = 0; c < C; ++c) {
+        const float y = sY[dl * CP + c];
+        mx = fmaxf(mx, -(y - 1.0f) * (y - 1.0f) / p.temperature);
+      }
+      float sum = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float y = sY[dl * CP + c];
+        sum += expf(-(y - 1.0f) * (y - 1.0f) / p.temperature - mx);
+      }
+      const size_t o = (((size_t)k * p.D + d0 + dl) * p.N + n) * C;
+      for (int c = 0; c < C; ++c) {
+        const float y = sY[dl * CP + c];
+        p.prob_out[o + c] = expf(-(y - 1.0f) * (y - 1.0f) / p.temperature - mx) / sum;
+      }
+    }
+  }
+  if (MODE == kFinal) return;
+
+  // ---------------- head: h1 of the next step for the same rows ----------------
+  // thread owns 8 consecutive features; their per-column constants stay in registers across draws
+  const float* xfrow = p.xf + ((size_t)k * p.N + n) * p.Fin;
+  const float* urow = p.u + ((size_t)k * p.N + n) * p.Fp;
+  for (int f0 = tid * 8; f0 < p.Fp; f0 += kTailThreads * 8) {
+    float a1[8], c1[8], uu[8], xx[8], w1[8][CP];
+    {
+      const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.A1[k] + f0));
+      const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.A1[k] + f0 + 4));
+      a1[0] = t0.x; a1[1] = t0.y; a1[2] = t0.z; a1[3] = t0.w; a1[4] = t1.x; a1[5] = t1.y; a1[6] = t1.z; a1[7] = t1.w;
+      const float4 q0 = __ldg(reinterpret_cast<const float4*>(p.C1[k] + f0));
+      const float4 q1 = __ldg(reinterpret_cast<const float4*>(p.C1[k] + f0 + 4));
+      c1[0] = q0.x; c1[1] = q0.y; c1[2] = q0.z; c1[3] = q0.w; c1[4] = q1.x; c1[5] = q1.y; c1[6] = q1.z; c1[7] = q1.w;
+      const float4 u0 = __ldg(reinterpret_cast<const float4*>(urow + f0));
+      const float4 u1 = __ldg(reinterpret_cast<const float4*>(urow + f0 + 4));
+      uu[0] = u0.x; uu[1] = u0.y; uu[2] = u0.z; uu[3] = u0.w; uu[4] = u1.x; uu[5] = u1.y; uu[6] = u1.z; uu[7] = u1.w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xx[j] = (f0 + j) < p.Fin ? __ldg(xfrow + f0 + j) : 0.f;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) w1[j][c] = __ldg(p.W1y[k] + (size_t)(f0 + j) * CP + c);
+      }
+    }
+    for (int dl = 0; dl < nd; ++dl) {
+      float yv[CP];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) yv[c] = c < C ? sY[dl * CP + c] : 0.f;
+      float hv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float lin = uu[j];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) lin = fmaf(w1[j][c], yv[c], lin);
+        hv[j] = softplus_log2dom(fmaf(a1[j], lin, c1[j])) * xx[j];
+      }
+      uint4 o;
+      o.x = Pack16<T16>::pack(hv[0], hv[1]);
+      o.y = Pack16<T16>::pack(hv[2], hv[3]);
+      o.z = Pack16<T16>::pack(hv[4], hv[5]);
+      o.w = Pack16<T16>::pack(hv[6], hv[7]);
+      const size_t grow = (size_t)k * p.rows_pad + (size_t)n * p.D + d0 + dl;
+      *reinterpret_cast<uint4*>(reinterpret_cast<T16*>(p.h1) + grow * p.Fp + f0) = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+cudaError_t resolve_encode(ladine_handle* h, std::string* err) {
+  if (h->encode_tiled) return cudaSuccess;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    *err = "cuTensorMapEncodeTiled is not available from the driver";
+    return e != cudaSuccess ? e : cudaErrorNotSupported;
+  }
+  h->encode_tiled = fn;
+  return cudaSuccess;
+}
+
+// 2-D K-major tensor map: inner dim = cols (contiguous), outer = rows; box = 64 x box_rows; 128B swizzle
+bool make_tmap(ladine_handle* h, CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+               bool bf16, std::string* err) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(h->encode_tiled)(
+      out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims,
+      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box_rows=%u", (int)r,
+             (unsigned long long)rows, (unsigned long long)cols, box_rows);
+    *err = buf;
+    return false;
+  }
+  return true;
+}
+
+// instruction descriptor for kind::f16 (PTX ISA "Instruction descriptor"): D format F32 (1) at [4,6);
+// A/B format (0 = F16, 1 = BF16) at [7,10)/[10,13); A,B K-major (0) at 15/16; N>>3 at [17,23); M>>4 at [24,29)
+uint32_t make_idesc(bool bf16) {
+  const uint32_t fmt = bf16 ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int LAYER, typename T16, int CP>
+cudaError_t launch_gemm_t(const GemmParams& p, int grid, cudaStream_t st) {
+  const size_t smem = tensor_gemm_smem_bytes(CP);
+  auto kern = trunk_gemm_kernel<LAYER, T16, CP>;
+  // cheap (host-side table update); done per launch so it is right for every device of the process
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kGemmThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int LAYER>
+cudaError_t launch_gemm(const GemmParams& p, int grid, bool bf16, int Cp, cudaStream_t st) {
+#define LADINE_GEMM_CASE(CPV)                                                              \
+  case CPV:                                                                                \
+    return bf16 ? launch_gemm_t<LAYER, __nv_bfloat16, CPV>(p, grid, st)                    \
+                : launch_gemm_t<LAYER, __half, CPV>(p, grid, st);
+  if (LAYER == 2) Cp = 2;  // the layer-2 epilogue does not depend on the class count
+  switch (Cp) {
+    LADINE_GEMM_CASE(2)
+    LADINE_GEMM_CASE(4)
+    LADINE_GEMM_CASE(8)
+    LADINE_GEMM_CASE(16)
+  }
+#undef LADINE_GEMM_CASE
+  return cudaErrorInvalidValue;
+}
+
+template <int MODE>
+cudaError_t launch_tail(const TailHeadParams& p, dim3 grid, bool bf16, int Cp, cudaStream_t st) {
+#define LADINE_TAIL_CASE(CPV)                                                              \
+  case CPV:                                                                                \
+    if (bf16) tailhead_kernel<MODE, __nv_bfloat16, CPV><<<grid, kTailThreads, 0, st>>>(p); \
+    else tailhead_kernel<MODE, __half, CPV><<<grid, kTailThreads, 0, st>>>(p);             \
+    break;
+  switch (Cp) {
+    LADINE_TAIL_CASE(2)
+    LADINE_TAIL_CASE(4)
+    LADINE_TAIL_CASE(8)
+    LADINE_TAIL_CASE(16)
+    default: return cudaErrorInvalidValue;
+  }
+#undef LADINE_TAIL_CASE
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t tensor_gemm_smem_bytes(int Cp) {
+  return 1024 /*alignment slack*/ + (size_t)kStages * kStageBytes + sizeof(float) * BN * (2 + Cp) + sizeof(GemmBarriers);
+}
+
+cudaError_t launch_tensor_chain(ladine_handle* h, const ladine_member* const* members, const ladine_sample_args& a,
+                                const ChainIds& ids, const StepCoef* h_coef, const TensorWorkspace& ws, int n_slots,
+                                int n_traj, cudaStream_t st, int64_t* launches, std::string* err) {
+  const ladine_member* m0 = members[0];
+  const bool bf16 = m0->precision == LADINE_PREC_BF16;
+  const int Fp = m0->Fp, Cp = m0->Cp, K = a.K;
+  const int rows = a.N * a.D;
+  const int mblk = (rows + BM - 1) / BM;
+  const int rows_pad = mblk * BM;
+  const size_t m_total = (size_t)K * rows_pad;
+
+  cudaError_t e = resolve_encode(h, err);
+  if (e != cudaSuccess) return e;
+
+  GemmParams g2{}, g3{};
+  if (!make_tmap(h, &g2.tmA, ws.h1, m_total, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
+  if (!make_tmap(h, &g3.tmA, ws.h2, m_total, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
+  for (int k = 0; k < K; ++k) {
+    if (!make_tmap(h, &g2.tmB[k], members[k]->W2h, Fp, Fp, BN, bf16, err)) return cudaErrorInvalidValue;
+    if (!make_tmap(h, &g3.tmB[k], members[k]->W3h, Fp, Fp, BN, bf16, err)) return cudaErrorInvalidValue;
+    g3.W4[k] = members[k]->W4;
+  }
+  for (GemmParams* g : {&g2, &g3}) {
+    g->Fp = Fp;
+    g->NB = Fp / BN;
+    g->KB = Fp / BK;
+    g->mblk = mblk;
+    g->rows = rows;
+    g->rows_pad = rows_pad;
+    g->num_tiles = K * mblk * (Fp / BN);
+    g->idesc = make_idesc(bf16);
+  }
+  g2.h_out = ws.h2;
+  g3.part = ws.part;
+  const int grid = g2.num_tiles < h->sm_count ? g2.num_tiles : h->sm_count;
+
+  TailHeadParams tp{};
+  for (int k = 0; k < K; ++k) {
+    tp.W1y[k] = members[k]->W1y;
+    tp.b4[k] = members[k]->b4;
+  }
+  tp.part = ws.part;
+  tp.ybuf = ws.ybuf;
+  tp.xf = a.xf;
+  tp.u = ws.u;
+  tp.ytmean = a.ytmean;
+  tp.y_init = a.y_init;
+  tp.noise = a.noise;
+  tp.h1 = ws.h1;
+  tp.y_out = a.y_out;
+  tp.traj_out = a.traj_out;
+  tp.prob_out = a.prob_out;
+  tp.temperature = a.prob_out ? a.temperature : 1.0f;
+  tp.seed = a.seed;
+  tp.ids = ids;
+  tp.N = a.N;
+  tp.D = a.D;
+  tp.C = m0->C;
+  tp.Fin = m0->F;
+  tp.Fp = Fp;
+  tp.NB = Fp / BN;
+  tp.rows_pad = rows_pad;
+  tp.n_slots = n_slots;
+  tp.n_traj = n_traj;
+  tp.dchunk = a.D < kTailMaxRows ? a.D : kTailMaxRows;
+  const dim3 tgrid(a.N, K, (a.D + tp.dchunk - 1) / tp.dchunk);
+  const int slot_base = a.y_init ? 0 : 1;
+
+  auto set_head_rows = [&](int t_next) {
+    for (int k = 0; k < K; ++k) {
+      tp.A1[k] = members[k]->A[0] + (size_t)t_next * Fp;
+      tp.C1[k] = members[k]->Cc[0] + (size_t)t_next * Fp;
+    }
+  };
+
+  // y_T (or the caller's y) and h1 for the first step
+  set_head_rows(a.t_first);
+  tp.slot = 0;
+  tp.traj_entry = a.y_init ? -1 : 0;
+  tp.write_out = 0;
+  e = launch_tail<kInit>(tp, tgrid, bf16, Cp, st);
+  if (e != cudaSuccess) return e;
+  ++*launches;
+
+  for (int t = a.t_first; t >= a.t_last; --t) {
+    for (int k = 0; k < K; ++k) {
+      g2.scale[k] = members[k]->A[1] + (size_t)t * Fp;
+      g2.shift[k] = members[k]->Cc[1] + (size_t)t * Fp;
+      g3.scale[k] = members[k]->A[2] + (size_t)t * Fp;
+      g3.shift[k] = members[k]->Cc[2] + (size_t)t * Fp;
+    }
+    e = launch_gemm<2>(g2, grid, bf16, Cp, st);
+    if (e != cudaSuccess) return e;
+    e = launch_gemm<3>(g3, grid, bf16, Cp, st);
+    if (e != cudaSuccess) return e;
+    tp.coef = h_coef[t];
+    tp.t = t;
+    tp.slot = slot_base + (a.t_first - t);
+    tp.traj_entry = slot_base + (a.t_first - t);
+    const bool last = (t == a.t_last);
+    tp.write_out = last ? 1 : 0;
+    if (last) {
+      e = launch_tail<kFinal>(tp, tgrid, bf16, Cp, st);
+    } else {
+      set_head_rows(t - 1);
+      e = launch_tail<kMid>(tp, tgrid, bf16, Cp, st);
+    }
+    if (e != cudaSuccess) return e;
+    *launches += 3;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int layer, int t, const void* h_in, int rows,
+                               void* h_out, float* part, cudaStream_t st, std::string* err) {
+  const bool bf16 = m->precision == LADINE_PREC_BF16;
+  cudaError_t e = resolve_encode(h, err);
+  if (e != cudaSuccess) return e;
+  const int Fp = m->Fp;
+  const int mblk = (rows + BM - 1) / BM;
+  GemmParams g{};
+  if (!make_tmap(h, &g.tmA, h_in, (uint64_t)mblk * BM, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
+  if (!make_tmap(h, &g.tmB[0], layer == 2 ? m->W2h : m->W3h, Fp, Fp, BN, bf16, err)) return cudaErrorInvalidValue;
+  g.scale[0] = m->A[layer - 1] + (size_t)t * Fp;
+  g.shift[0] = m->Cc[layer - 1] + (size_t)t * Fp;
+  g.W4[0] = m->W4;
+  g.h_out = h_out;
+  g.part = part;
+  g.Fp = Fp;
+  g.NB = Fp / BN;
+  g.KB = Fp / BK;
+  g.mblk = mblk;
+  g.rows = rows;
+  g.rows_pad = mblk * BM;
+  g.num_tiles = mblk * g.NB;
+  g.idesc = make_idesc(bf16);
+  const int grid = g.num_tiles < h->sm_count ? g.num_tiles : h->sm_count;
+  return layer == 2 ? launch_gemm<2>(g, grid, bf16, m->Cp, st) : launch_gemm<3>(g, grid, bf16, m->Cp, st);
+}
+
+}  // namespace ladine

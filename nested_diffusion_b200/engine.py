@@ -1,0 +1,264 @@
+"""Host side of the fused sampler: member packing and the batched ``sample_chains`` call.
+
+PyTorch is used for device memory, streams and the step-invariant encoder GEMMs only; every
+reverse step runs inside libladine (C ABI in include/ladine.h).  Nothing here falls back to
+PyTorch arithmetic for the reverse process.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _capi
+from .schedule import coef_table
+
+_TRUNK_KEYS = ("lin1.lin.weight", "lin1.lin.bias", "lin2.lin.weight", "lin2.lin.bias", "lin3.lin.weight",
+               "lin3.lin.bias", "lin4.weight", "lin4.bias", "lin1.embed.weight", "lin2.embed.weight",
+               "lin3.embed.weight")
+
+
+def _device_index(device: torch.device) -> int:
+    if device.type != "cuda":
+        raise RuntimeError(
+            "the LaDiNE sampler runs only on a CUDA (sm_100a) device; there is no CPU fallback "
+            f"(got tensors on {device})")
+    return device.index if device.index is not None else torch.cuda.current_device()
+
+
+class PackedMember:
+    """One ensemble member folded and re-laid-out on the device (ladine_pack_member)."""
+
+    def __init__(self, state_dict, n_steps: Optional[int] = None, precision: str = "auto", bn_eps: float = 1e-5):
+        sd = {k: v.detach() for k, v in state_dict.items() if k.startswith(("lin", "unetnorm"))}
+        missing = [k for k in _TRUNK_KEYS if k not in sd]
+        if missing:
+            raise ValueError(f"state_dict lacks ConditionalModel trunk keys: {missing}")
+        w1 = sd["lin1.lin.weight"]
+        dev = w1.device
+        self.device_index = _device_index(dev)
+        self.device = torch.device("cuda", self.device_index)
+        F_dim, in1 = w1.shape
+        C_cls = sd["lin4.weight"].shape[0]
+        if in1 not in (C_cls, 2 * C_cls):
+            raise ValueError(f"lin1 expects {in1} inputs, which is neither num_classes nor 2*num_classes ({C_cls})")
+        if C_cls > _capi.LADINE_MAX_CLASSES:
+            raise NotImplementedError(f"num_classes={C_cls} > {_capi.LADINE_MAX_CLASSES} is not accelerated")
+        emb_rows = sd["lin1.embed.weight"].shape[0]
+        self.T = int(n_steps) if n_steps is not None else emb_rows - 1  # tables hold timesteps+1 rows
+        if not (1 <= self.T <= emb_rows):
+            raise ValueError(f"n_steps={self.T} outside the gamma table ({emb_rows} rows)")
+        if precision not in _capi.PREC:
+            raise ValueError(f"precision must be one of {sorted(_capi.PREC)}")
+        self.F, self.C, self.guidance = int(F_dim), int(C_cls), in1 == 2 * C_cls
+
+        def f32(name, shape):
+            t = sd[name]
+            if tuple(t.shape) != tuple(shape):
+                raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+            if t.device != dev:
+                raise ValueError(f"{name} is on {t.device}, expected {dev}")
+            return t.to(torch.float32).contiguous()
+
+        keep = []  # keep the FP32 sources alive until the pack kernels have run
+
+        def ptr(name, shape):
+            t = f32(name, shape)
+            keep.append(t)
+            return t.data_ptr()
+
+        d = _capi.MemberDesc()
+        d.struct_size = C.sizeof(_capi.MemberDesc)
+        d.feature_dim, d.num_classes, d.n_steps, d.emb_rows = self.F, self.C, self.T, emb_rows
+        d.guidance, d.precision, d.bn_eps = int(self.guidance), _capi.PREC[precision], bn_eps
+        Fd = self.F
+        d.lin1_w, d.lin1_b = ptr("lin1.lin.weight", (Fd, in1)), ptr("lin1.lin.bias", (Fd,))
+        d.lin2_w, d.lin2_b = ptr("lin2.lin.weight", (Fd, Fd)), ptr("lin2.lin.bias", (Fd,))
+        d.lin3_w, d.lin3_b = ptr("lin3.lin.weight", (Fd, Fd)), ptr("lin3.lin.bias", (Fd,))
+        d.lin4_w, d.lin4_b = ptr("lin4.weight", (self.C, Fd)), ptr("lin4.bias", (self.C,))
+        for l in range(3):
+            d.emb[l] = ptr(f"lin{l + 1}.embed.weight", (emb_rows, Fd))
+            d.bn_w[l] = ptr(f"unetnorm{l + 1}.weight", (Fd,))
+            d.bn_b[l] = ptr(f"unetnorm{l + 1}.bias", (Fd,))
+            d.bn_mean[l] = ptr(f"unetnorm{l + 1}.running_mean", (Fd,))
+            d.bn_var[l] = ptr(f"unetnorm{l + 1}.running_var", (Fd,))
+
+        lib = _capi.load()
+        self._h = _capi.handle(self.device_index)
+        out = C.c_void_p()
+        with torch.cuda.device(self.device_index):
+            stream = torch.cuda.current_stream().cuda_stream
+            _capi.check(self._h, lib.ladine_pack_member(self._h, C.byref(d), C.c_void_p(stream), C.byref(out)))
+            torch.cuda.current_stream().synchronize()  # sources may now be released
+        del keep
+        self._ptr = out.value
+        self.precision = _capi.PREC_NAME[lib.ladine_member_precision(self._ptr)]
+        self.Fp = lib.ladine_member_fpad(self._ptr)
+        self.Cp = lib.ladine_member_cpad(self._ptr)
+        self.nbytes = int(lib.ladine_member_bytes(self._ptr))
+        self._finalizer = weakref.finalize(self, lib.ladine_free_member, self._h, self._ptr)
+
+    @property
+    def ptr(self) -> int:
+        return self._ptr
+
+
+# ------------------------------------------------------------------------------------------------
+# module -> PackedMember cache (re-packed when any trunk parameter is modified in place or moved)
+# ------------------------------------------------------------------------------------------------
+_PACK_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _trunk_fingerprint(model) -> tuple:
+    sd = model.state_dict(keep_vars=True)
+    return tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in sd.items()
+                 if k.startswith(("lin", "unetnorm")) and v.is_floating_point())
+
+
+def packed_member_of(model, precision: str = "auto") -> PackedMember:
+    """Pack ``model`` (a ConditionalModel-shaped nn.Module) once and reuse it across calls."""
+    if isinstance(model, PackedMember):
+        return model
+    fp = (_trunk_fingerprint(model), precision)
+    hit = _PACK_CACHE.get(model)
+    if hit is not None and hit[0] == fp:
+        return hit[1]
+    pm = PackedMember(model.state_dict(), precision=precision)
+    _PACK_CACHE[model] = (fp, pm)
+    return pm
+
+
+def encode_features(model, x: torch.Tensor) -> torch.Tensor:
+    """``norm(encoder_x(x))`` in PyTorch (step-invariant; latent_model.py:170-171)."""
+    with torch.no_grad():
+        if hasattr(model, "encode"):
+            return model.encode(x)
+        return model.norm(model.encoder_x(x))
+
+
+def fresh_seed() -> int:
+    """A Philox key drawn from torch's default CPU generator, so ``torch.manual_seed`` makes runs repeatable."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def _as_f32(t: torch.Tensor, shape, name: str, device) -> torch.Tensor:
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    if t.device != device:
+        raise ValueError(f"{name} is on {t.device}, expected {device}")
+    return t.detach().to(torch.float32).contiguous()
+
+
+def n_noise_slots(T_first: int, t_last: int, has_init: bool) -> int:
+    steps = T_first - t_last + 1
+    return (0 if has_init else 1) + steps - (1 if t_last == 0 else 0)
+
+
+def sample_chains(members: Sequence[PackedMember], xf: torch.Tensor, y0hat: torch.Tensor, ytmean: torch.Tensor,
+                  coef: torch.Tensor, draws: int = 1, *, t_first: Optional[int] = None, t_last: int = 0,
+                  y_init: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None, seed: int = 0,
+                  member_ids: Optional[Sequence[int]] = None, image_offset: int = 0, images_total: int = 0,
+                  draw_offset: int = 0, draws_total: int = 0, trajectory: bool = False,
+                  temperature: Optional[float] = None):
+    """One ``ladine_sample`` call: K members x ``draws`` x N images, steps t_first .. t_last.
+
+    xf [K,N,F], y0hat/ytmean [K,N,C] (CUDA, FP32); coef: HOST [T,8] from ``schedule.coef_table``.
+    Returns ``y`` [K,D,N,C] (plus ``traj`` [K,D,n_traj,N,C] and/or ``probs`` [K,D,N,C] when asked),
+    enqueued on the current CUDA stream without host synchronisation.
+    """
+    K = len(members)
+    if K < 1:
+        raise ValueError("need at least one member")
+    m0 = members[0]
+    dev = m0.device
+    for m in members:
+        if (m.F, m.C, m.precision, m.guidance, m.device) != (m0.F, m0.C, m0.precision, m0.guidance, dev):
+            raise ValueError("members of one call must share feature_dim, num_classes, guidance, precision, device")
+    if xf.dim() != 3:
+        raise ValueError("xf must be [K, N, F]")
+    N = xf.shape[1]
+    D = int(draws)
+    T = coef.shape[0]
+    if coef.device.type != "cpu" or coef.dtype != torch.float32 or coef.shape[1] != 8 or not coef.is_contiguous():
+        raise ValueError("coef must be a contiguous HOST float32 [T, 8] table (schedule.coef_table)")
+    if min(m.T for m in members) < T:
+        raise ValueError(f"schedule has {T} steps but a member's gamma tables hold fewer rows")
+    t_first = T - 1 if t_first is None else int(t_first)
+    xf = _as_f32(xf, (K, N, m0.F), "xf", dev)
+    y0hat = _as_f32(y0hat, (K, N, m0.C), "y_0_hat", dev)
+    ytmean = _as_f32(ytmean, (K, N, m0.C), "y_T_mean", dev)
+    n_slots = n_noise_slots(t_first, t_last, y_init is not None)
+    n_traj = (0 if y_init is not None else 1) + (t_first - t_last + 1)
+    if y_init is not None:
+        y_init = _as_f32(y_init, (K, D, N, m0.C), "y_init", dev)
+    if noise is not None:
+        noise = _as_f32(noise, (K, D, n_slots, N, m0.C), "noise", dev)
+
+    y_out = torch.empty((K, D, N, m0.C), dtype=torch.float32, device=dev)
+    traj = torch.empty((K, D, n_traj, N, m0.C), dtype=torch.float32, device=dev) if trajectory else None
+    probs = torch.empty_like(y_out) if temperature is not None else None
+
+    a = _capi.SampleArgs()
+    a.struct_size = C.sizeof(_capi.SampleArgs)
+    a.K, a.N, a.D, a.T, a.t_first, a.t_last = K, N, D, T, t_first, int(t_last)
+    a.xf, a.y0hat, a.ytmean = xf.data_ptr(), y0hat.data_ptr(), ytmean.data_ptr()
+    a.y_init = y_init.data_ptr() if y_init is not None else None
+    a.coef = coef.data_ptr()
+    a.noise = noise.data_ptr() if noise is not None else None
+    a.seed = int(seed) & (2 ** 64 - 1)
+    ids = None
+    if member_ids is not None:
+        if len(member_ids) != K:
+            raise ValueError("member_ids must have one entry per member")
+        ids = (C.c_int32 * K)(*[int(i) for i in member_ids])
+        a.member_ids = C.cast(ids, C.POINTER(C.c_int32))
+    a.image_offset, a.images_total = int(image_offset), int(images_total)
+    a.draw_offset, a.draws_total = int(draw_offset), int(draws_total)
+    a.y_out = y_out.data_ptr()
+    a.traj_out = traj.data_ptr() if traj is not None else None
+    a.prob_out = probs.data_ptr() if probs is not None else None
+    a.temperature = float(temperature) if temperature is not None else 1.0
+
+    lib = _capi.load()
+    h = _capi.handle(m0.device_index)
+    arr = (C.c_void_p * K)(*[m.ptr for m in members])
+    with torch.cuda.device(m0.device_index):
+        a.stream = torch.cuda.current_stream().cuda_stream
+        _capi.check(h, lib.ladine_sample(h, arr, C.byref(a)))
+    out = {"y": y_out}
+    if traj is not None:
+        out["traj"] = traj
+    if probs is not None:
+        out["probs"] = probs
+    return out
+
+
+def last_launches(device_index: int) -> int:
+    return int(_capi.load().ladine_last_launches(_capi.handle(device_index)))
+
+
+def fill_noise(device, K, N, D, C_cls, T, seed, *, t_first=None, t_last=0, has_init=False, member_ids=None,
+               image_offset=0, images_total=0, draw_offset=0, draws_total=0) -> torch.Tensor:
+    """The N(0,1) draws ``sample_chains(noise=None, seed=seed)`` uses, as a [K,D,S,N,C] tensor."""
+    device = torch.device(device)
+    di = _device_index(device)
+    t_first = T - 1 if t_first is None else t_first
+    S = n_noise_slots(t_first, t_last, has_init)
+    out = torch.empty((K, D, S, N, C_cls), dtype=torch.float32, device=torch.device("cuda", di))
+    a = _capi.SampleArgs()
+    a.struct_size = C.sizeof(_capi.SampleArgs)
+    a.K, a.N, a.D, a.T, a.t_first, a.t_last = K, N, D, T, t_first, t_last
+    a.seed = int(seed) & (2 ** 64 - 1)
+    a.y_init = 1 if has_init else None  # only its null-ness matters here
+    if member_ids is not None:
+        ids = (C.c_int32 * K)(*[int(i) for i in member_ids])
+        a.member_ids = C.cast(ids, C.POINTER(C.c_int32))
+    a.image_offset, a.images_total, a.draw_offset, a.draws_total = image_offset, images_total, draw_offset, draws_total
+    lib = _capi.load()
+    h = _capi.handle(di)
+    with torch.cuda.device(di):
+        a.stream = torch.cuda.current_stream().cuda_stream
+        _capi.check(h, lib.ladine_fill_noise(h, C.byref(a), C_cls, C.c_void_p(out.data_ptr())))
+    return out

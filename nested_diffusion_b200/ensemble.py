@@ -1,0 +1,145 @@
+"""Nested-ensemble driver: every member x posterior draw x image in one batched call, sharded over
+the GPUs of one node by image tile, with a single all-gather of the per-draw class probabilities.
+
+Replaces the loop at classification_train_separately.py:764-784 (K members x 20 sequential
+``p_sample_loop`` calls on the same images, members shuttled CPU<->GPU, samples moved to the CPU one
+by one).  Chains are independent, so sharding needs no data-path collective; the only exchange is
+the gather that feeds the ensemble statistics.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import engine
+from .schedule import coef_table
+
+
+def shard_bounds(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced partition of ``range(n_items)``: the first ``n_items % world`` ranks get one extra."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("need 0 <= rank < world")
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def padded_shard_size(n_items: int, world: int) -> int:
+    return -(-n_items // world)
+
+
+def gather_image_shards(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor:
+    """All-gather per-rank tensors ``[n_local, ...]`` (image-major) into ``[n_items, ...]`` on every rank.
+
+    Equal-count collective: shards are zero-padded to ``ceil(n_items / world)`` rows, gathered with one
+    ``all_gather_into_tensor`` (NCCL over NVLink on the B200 box, gloo in the CPU tests) and trimmed."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        if local.shape[0] != n_items:
+            raise ValueError("no process group: the local shard must hold every image")
+        return local
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lo, hi = shard_bounds(n_items, rank, world)
+    if local.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank} should hold {hi - lo} images, got {local.shape[0]}")
+    per = padded_shard_size(n_items, world)
+    send = local.new_zeros((per,) + tuple(local.shape[1:]))
+    send[: hi - lo] = local
+    recv = local.new_empty((world * per,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+    parts = []
+    for r in range(world):
+        rlo, rhi = shard_bounds(n_items, r, world)
+        parts.append(recv[r * per: r * per + (rhi - rlo)])
+    return torch.cat(parts, dim=0)
+
+
+@dataclass
+class EnsembleResult:
+    y0: torch.Tensor                 # [K, D, N_local, C] final y_0 of every chain of this rank's images
+    probs: Optional[torch.Tensor]    # [K, D, N_local, C] softmax(-(y_0-1)^2 / temperature), if asked
+    image_range: Tuple[int, int]     # global [lo, hi) of the images held by this rank
+
+
+class NestedEnsemble:
+    """K packed members kept resident on one GPU (no per-batch CPU<->GPU shuttle)."""
+
+    def __init__(self, models: Sequence, precision: str = "auto", member_ids: Optional[Sequence[int]] = None):
+        if len(models) < 1:
+            raise ValueError("need at least one member")
+        self.models = list(models)
+        self.members: List[engine.PackedMember] = [engine.packed_member_of(m, precision) for m in models]
+        self.member_ids = list(member_ids) if member_ids is not None else list(range(len(models)))
+        self.device = self.members[0].device
+
+    @property
+    def K(self) -> int:
+        return len(self.members)
+
+    def encode(self, x: torch.Tensor) -> torch.Tensor:
+        """[K, N, F] step-invariant features, one encoder pass per member (PyTorch GEMMs)."""
+        return torch.stack([engine.encode_features(m, x) for m in self.models])
+
+    def sample(self, x: torch.Tensor, y0hats, draws: int, n_steps: int, alphas, one_minus_alphas_bar_sqrt, *,
+               y_T_means=None, noise: Optional[torch.Tensor] = None, seed: Optional[int] = None,
+               temperature: Optional[float] = None, xf: Optional[torch.Tensor] = None, image_offset: int = 0,
+               images_total: int = 0, draw_offset: int = 0, draws_total: int = 0) -> EnsembleResult:
+        """All K x ``draws`` chains for the images in ``x`` ([N, ...]); ``y0hats``: [K, N, C] or list of K [N, C]."""
+        y0hats = torch.stack(list(y0hats)) if not torch.is_tensor(y0hats) else y0hats
+        mus = y0hats if y_T_means is None else (
+            torch.stack(list(y_T_means)) if not torch.is_tensor(y_T_means) else y_T_means)
+        if xf is None:
+            xf = self.encode(x)
+        if noise is None and seed is None:
+            seed = engine.fresh_seed()
+        coef = coef_table(alphas, one_minus_alphas_bar_sqrt, n_steps)
+        out = engine.sample_chains(self.members, xf, y0hats, mus, coef, draws, noise=noise, seed=seed or 0,
+                                   member_ids=self.member_ids, image_offset=image_offset, images_total=images_total,
+                                   draw_offset=draw_offset, draws_total=draws_total, temperature=temperature)
+        n = xf.shape[1]
+        return EnsembleResult(out["y"], out.get("probs"), (image_offset, image_offset + n))
+
+
+def sample_ensemble(models_or_ensemble, x, y0hats, draws, n_steps, alphas, one_minus_alphas_bar_sqrt, *,
+                    seed: Optional[int] = None, temperature: Optional[float] = None, group=None,
+                    precision: str = "auto"):
+    """Sharded nested-ensemble sampling + the single all-gather.
+
+    Every rank passes the SAME full ``x`` [N, ...] and ``y0hats`` [K, N, C]; each samples its image
+    tile (``shard_bounds``) for all members and draws with Philox streams keyed on global
+    (member, draw, image) ids -- so the gathered result is identical for any world size -- and
+    returns on every rank ``(y0 [N, K*D, C], probs [N, K*D, C] or None)`` in image-major order."""
+    import torch.distributed as dist
+
+    ens = models_or_ensemble if isinstance(models_or_ensemble, NestedEnsemble) else NestedEnsemble(
+        models_or_ensemble, precision)
+    y0hats = torch.stack(list(y0hats)) if not torch.is_tensor(y0hats) else y0hats
+    N = x.shape[0]
+    distributed = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if distributed else 1
+    rank = dist.get_rank(group) if distributed else 0
+    if seed is None:
+        seed = engine.fresh_seed()
+        if distributed:  # all ranks must agree on the key
+            box = [seed]
+            dist.broadcast_object_list(box, src=0, group=group)
+            seed = box[0]
+    lo, hi = shard_bounds(N, rank, world)
+    K, D = ens.K, int(draws)
+    C = y0hats.shape[-1]
+    if hi > lo:
+        res = ens.sample(x[lo:hi], y0hats[:, lo:hi], D, n_steps, alphas, one_minus_alphas_bar_sqrt, seed=seed,
+                         temperature=temperature, image_offset=lo, images_total=N)
+        y_local = res.y0.permute(2, 0, 1, 3).reshape(hi - lo, K * D, C)
+        p_local = res.probs.permute(2, 0, 1, 3).reshape(hi - lo, K * D, C) if res.probs is not None else None
+    else:
+        y_local = torch.empty((0, K * D, C), dtype=torch.float32, device=ens.device)
+        p_local = torch.empty_like(y_local) if temperature is not None else None
+    if p_local is not None:
+        both = gather_image_shards(torch.cat([y_local, p_local], dim=-1).contiguous(), N, group)
+        return both[..., :C].contiguous(), both[..., C:].contiguous()
+    return gather_image_shards(y_local.contiguous(), N, group), None

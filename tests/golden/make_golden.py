@@ -1,0 +1,213 @@
+"""Generate the golden vectors under tests/golden/ by running the REFERENCE ITSELF.
+
+Run in the build container only (it imports /root/reference/diffusion, which does not exist on
+the GPU box):
+
+    python tests/golden/make_golden.py            # all fixtures (~3-4 min on 8 cores)
+    python tests/golden/make_golden.py small ens  # a subset
+
+Every fixture records the reference's own ``p_sample_loop`` / ``p_sample`` output
+(diffusion_utils.py:54-163 driving latent_model.ConditionalModel, latent_model.py:108-184) on
+synthetic members built by ``oracle.ladine_oracle.synth_state_dict`` and loaded with the
+reference's ``load_state_dict``.  The noise the reference draws with ``torch.randn_like`` is captured
+by replaying the CPU generator (``torch.manual_seed(s)`` then ``randn`` in call order) and stored
+or re-derivable from the recorded seed.  Inputs that are small are stored verbatim; large ones are
+re-generated from the recorded seeds (torch CPU generator) and guarded by a checksum.
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference/diffusion")
+
+import diffusion_utils as ref_du  # noqa: E402  (the reference)
+import latent_model as ref_lm  # noqa: E402  (the reference)
+from oracle import ladine_oracle as orc  # noqa: E402
+
+
+def ns(**kw):
+    return argparse.Namespace(**kw)
+
+
+def ref_config(F, H, Dx, C, T):
+    return ns(diffusion=ns(timesteps=T), data=ns(num_classes=C, dataset="ChestXRay"),
+              model=ns(data_dim=Dx, arch="linear", feature_dim=F, hidden_dim=H))
+
+
+def ref_member(sd, F, H, Dx, C, T, guidance):
+    m = ref_lm.ConditionalModel(ref_config(F, H, Dx, C, T), guidance=guidance)
+    m.load_state_dict(sd)
+    return m.eval()
+
+
+def schedule(T, kind="linear", start=1e-4, end=0.02):
+    betas = ref_du.make_beta_schedule(schedule=kind, num_timesteps=T, start=start, end=end)
+    return orc.schedule_tensors(betas, kind)
+
+
+def digest(*tensors):
+    h = hashlib.sha256()
+    for t in tensors:
+        h.update(np.ascontiguousarray(t.detach().numpy()).tobytes())
+    return h.hexdigest()[:16]
+
+
+def sd_digest(sd):
+    return digest(*[sd[k].float() for k in sorted(sd)])
+
+
+def replay_noise(seed, n, shape):
+    torch.manual_seed(seed)
+    return torch.stack([torch.randn(*shape) for _ in range(n)])
+
+
+def save(name, meta, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, meta=np.array(json.dumps(meta)),
+                        **{k: v.detach().numpy() if torch.is_tensor(v) else v for k, v in arrays.items()})
+    print(f"  wrote {os.path.relpath(path, ROOT)}  ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+def chain_fixture(name, *, F, H, Dx, C, T, B, guidance=True, sd_seed, in_seed, noise_seed,
+                  store_inputs=False, eps_gain=1.0, keep=None, sched="linear"):
+    t0 = time.time()
+    sd = orc.synth_state_dict(sd_seed, F, H, Dx, C, T, guidance=guidance, eps_gain=eps_gain)
+    x, yhat = orc.synth_inputs(in_seed, B, Dx, C)
+    alphas, omabs = schedule(T, sched)
+    model = ref_member(sd, F, H, Dx, C, T, guidance)
+    with torch.no_grad():
+        torch.manual_seed(noise_seed)
+        seq = ref_du.p_sample_loop(model, x, yhat, yhat, T, alphas, omabs, only_last_sample=False)
+        torch.manual_seed(noise_seed)
+        last = ref_du.p_sample_loop(model, x, yhat, yhat, T, alphas, omabs, only_last_sample=True)
+    seq = torch.stack(seq)
+    assert torch.equal(seq[-1], last)
+    keep = list(range(T + 1)) if keep is None else sorted(set(k for k in keep if k <= T))
+    meta = dict(kind="chain", F=F, H=H, Dx=Dx, C=C, T=T, B=B, guidance=guidance, sd_seed=sd_seed,
+                in_seed=in_seed, noise_seed=noise_seed, eps_gain=eps_gain, keep=keep, sched=sched,
+                sd_digest=sd_digest(sd), in_digest=digest(x, yhat), stored_inputs=store_inputs,
+                ref="diffusion_utils.p_sample_loop + latent_model.ConditionalModel (torch %s)" % torch.__version__)
+    arrays = dict(traj=seq[keep], y0=last)
+    if store_inputs:
+        arrays.update({"sd/" + k: v for k, v in sd.items()})
+        arrays.update(x=x, yhat=yhat, noise=replay_noise(noise_seed, T, (B, C)))
+    save(name, meta, **arrays)
+    print(f"  {name}: |y0|max={last.abs().max():.3e}  {time.time() - t0:.1f}s")
+
+
+def ensemble_fixture(name, *, K, D, N, F, H, Dx, C, T, sd_seed0, in_seed, noise_seed):
+    """classification_train_separately.py:764-784 replayed with the reference functions."""
+    sds = [orc.synth_state_dict(sd_seed0 + k, F, H, Dx, C, T) for k in range(K)]
+    g = torch.Generator().manual_seed(in_seed)
+    x = torch.rand(N, Dx, generator=g)
+    y0hats = [torch.softmax(2 * torch.randn(N, C, generator=g), dim=1) for _ in range(K)]
+    alphas, omabs = schedule(T)
+    members = [ref_member(sd, F, H, Dx, C, T, True) for sd in sds]
+    samples = []
+    torch.manual_seed(noise_seed)
+    with torch.no_grad():
+        for ii in range(K):
+            for _ in range(D):
+                samples.append(ref_du.p_sample_loop(members[ii], x, y0hats[ii], y0hats[ii], T, alphas,
+                                                    omabs, only_last_sample=True))
+    y0 = torch.stack(samples).reshape(K, D, N, C)
+    meta = dict(kind="ensemble", K=K, D=D, N=N, F=F, H=H, Dx=Dx, C=C, T=T, sd_seed0=sd_seed0,
+                in_seed=in_seed, noise_seed=noise_seed, sd_digest=[sd_digest(s) for s in sds],
+                in_digest=digest(x, *y0hats))
+    save(name, meta, y0=y0)
+
+
+def shipped_dims_fixture(name, *, B=8, steps=(999, 500, 1), sd_seed=0, in_seed=5, noise_seed=123):
+    """Full shipped shape (chest_x_ray.yml:11-15): Dx=150528, H=F=4096, a few explicit p_sample
+    steps plus the final step, through the reference as written (2.59 GiB member)."""
+    F = H = 4096
+    Dx, C, T = 150528, 2, 1000
+    sd = orc.synth_state_dict(sd_seed, F, H, Dx, C, T)
+    x, yhat = orc.synth_inputs(in_seed, B, Dx, C)
+    alphas, omabs = schedule(T)
+    model = ref_member(sd, F, H, Dx, C, T, True)
+    g = torch.Generator().manual_seed(noise_seed)
+    y_in = yhat + torch.randn(B, C, generator=g)
+    outs, zs = [], []
+    with torch.no_grad():
+        for t in steps:
+            seed = noise_seed + t
+            torch.manual_seed(seed)
+            outs.append(ref_du.p_sample(model, x, y_in, yhat, yhat, t, alphas, omabs))
+            torch.manual_seed(seed)
+            zs.append(torch.randn(B, C))
+        y_last = ref_du.p_sample_t_1to0(model, x, y_in, yhat, yhat, omabs)
+        xf = model.norm(model.encoder_x(x))
+    meta = dict(kind="shipped_steps", F=F, H=H, Dx=Dx, C=C, T=T, B=B, steps=list(steps), sd_seed=sd_seed,
+                in_seed=in_seed, noise_seed=noise_seed, sd_digest="skipped(2.59GiB)", in_digest=digest(x, yhat))
+    save(name, meta, y_in=y_in, z=torch.stack(zs), y_out=torch.stack(outs), y_final=y_last,
+         xf_sample=xf[:, :64].contiguous())
+
+
+def schedules_fixture(name="schedules"):
+    """diffusion_utils.make_beta_schedule for every schedule kind + the runner's derived tensors."""
+    arrays = {}
+    for kind in ("linear", "const", "quad", "jsd", "sigmoid", "cosine", "cosine_reverse", "cosine_anneal"):
+        for T in (100, 1000):
+            arrays[f"{kind}/{T}"] = ref_du.make_beta_schedule(schedule=kind, num_timesteps=T, start=1e-4, end=0.02).float()
+    save(name, dict(kind="schedules", start=1e-4, end=0.02), **arrays)
+
+
+FIXTURES = {
+    "schedules": schedules_fixture,
+    # tiny, inputs stored verbatim, full trajectory
+    "small": lambda: chain_fixture("small_f128_t50", F=128, H=64, Dx=256, C=2, T=50, B=64, sd_seed=11,
+                                   in_seed=12, noise_seed=13, store_inputs=True),
+    # full-length chain on the SMEM-resident shape
+    "small1000": lambda: chain_fixture("small_f128_t1000", F=128, H=64, Dx=256, C=2, T=1000, B=64, sd_seed=21,
+                                       in_seed=22, noise_seed=23, keep=[0, 1, 2, 10, 100, 500, 900, 999, 1000]),
+    # tensor-core tile shapes, ragged row count
+    "f256": lambda: chain_fixture("tc_f256_t200", F=256, H=64, Dx=128, C=2, T=200, B=96, sd_seed=31,
+                                  in_seed=32, noise_seed=33, keep=[0, 1, 50, 199, 200]),
+    "f512": lambda: chain_fixture("tc_f512_t100", F=512, H=32, Dx=64, C=2, T=100, B=200, sd_seed=41,
+                                  in_seed=42, noise_seed=43, keep=[0, 1, 99, 100]),
+    # class-count / guidance variants
+    "c10": lambda: chain_fixture("c10_noguid_f64_t20", F=64, H=32, Dx=48, C=10, T=20, B=8, guidance=False,
+                                 sd_seed=51, in_seed=52, noise_seed=53, store_inputs=True),
+    "c3": lambda: chain_fixture("c3_f96_t40", F=96, H=32, Dx=48, C=3, T=40, B=33, sd_seed=61, in_seed=62,
+                                noise_seed=63),
+    # 'trained-like' scale: lin4 shrunk so eps, y_0 = O(1) and an absolute 1e-4 bar is meaningful
+    "trained": lambda: chain_fixture("trainedlike_f128_t1000", F=128, H=64, Dx=256, C=2, T=1000, B=64,
+                                     sd_seed=71, in_seed=72, noise_seed=73, eps_gain=0.02, keep=[0, 500, 1000]),
+    "trained_tc": lambda: chain_fixture("trainedlike_f256_t1000", F=256, H=64, Dx=128, C=2, T=1000, B=64,
+                                        sd_seed=75, in_seed=76, noise_seed=77, eps_gain=0.02, keep=[0, 500, 1000]),
+    # other schedule kind
+    "cosine": lambda: chain_fixture("cosine_f64_t60", F=64, H=32, Dx=48, C=2, T=60, B=16, sd_seed=81,
+                                    in_seed=82, noise_seed=83, sched="cosine"),
+    # nested ensemble loop
+    "ens": lambda: ensemble_fixture("ensemble_k3_d2", K=3, D=2, N=16, F=128, H=32, Dx=64, C=2, T=30,
+                                    sd_seed0=91, in_seed=92, noise_seed=93),
+    "ens_tc": lambda: ensemble_fixture("ensemble_tc_k2_d3", K=2, D=3, N=50, F=256, H=32, Dx=64, C=2, T=40,
+                                       sd_seed0=95, in_seed=96, noise_seed=97),
+    # shipped trunk width with a tiny encoder, full T=1000 (reference code, ~1 min)
+    "f4096": lambda: chain_fixture("trunk_f4096_t1000", F=4096, H=32, Dx=64, C=2, T=1000, B=64, sd_seed=101,
+                                   in_seed=102, noise_seed=103, keep=[0, 1, 500, 999, 1000]),
+    "f4096_trained": lambda: chain_fixture("trunk_f4096_t1000_trainedlike", F=4096, H=32, Dx=64, C=2, T=1000,
+                                           B=64, sd_seed=111, in_seed=112, noise_seed=113, eps_gain=0.02,
+                                           keep=[0, 500, 1000]),
+    # full shipped dims, explicit steps
+    "shipped": lambda: shipped_dims_fixture("shipped_dims_steps"),
+}
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    names = sys.argv[1:] or list(FIXTURES)
+    for n in names:
+        print(f"[{n}]")
+        FIXTURES[n]()

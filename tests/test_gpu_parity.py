@@ -1,0 +1,269 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the reference's golden outputs and the oracle.
+
+Tolerances (max-abs relative to max(1, ||y_ref||_inf); stated here, used below):
+  FP32 SMEM-resident path ........ 1e-5   vs the reference's own p_sample_loop output
+  FP16 tensor path ............... 5e-4   vs the reference;  2e-5 vs the oracle's FP16-operand emulation
+  BF16 tensor path ............... 4e-3   vs the reference;  2e-5 vs the oracle's BF16-operand emulation
+and argmax labels identical wherever the reference's top-2 margin exceeds the tolerance band.
+"""
+import argparse
+
+import pytest
+import torch
+
+from oracle import ladine_oracle as orc
+from tests.golden_util import ChainFixture, EnsembleFixture, Fixture, names, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-5, "fp16": 5e-4, "bf16": 4e-3}
+TOL_EMU = 2e-5
+ODT = {"fp16": torch.float16, "bf16": torch.bfloat16}
+
+
+def _ns(**kw):
+    return argparse.Namespace(**kw)
+
+
+def make_model(meta, sd, device="cuda"):
+    import nested_diffusion_b200 as nd
+
+    cfg = _ns(diffusion=_ns(timesteps=meta["T"]), data=_ns(num_classes=meta["C"], dataset="ChestXRay"),
+              model=_ns(data_dim=meta["Dx"], arch="linear", feature_dim=meta["F"], hidden_dim=meta["H"]))
+    m = nd.ConditionalModel(cfg, guidance=meta.get("guidance", True))
+    m.load_state_dict(sd)
+    return m.eval().to(device)
+
+
+def labels_match(y, ref, band):
+    """argmax equal on every row whose reference top-2 margin is larger than the tolerance band."""
+    top2 = ref.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > band
+    return bool((y.argmax(1)[safe] == ref.argmax(1)[safe]).all()), int(safe.sum())
+
+
+def precisions_for(F):
+    return ["fp32"] if F <= 128 else ["fp16", "bf16"]
+
+
+CHAINS = [n for n in names("chain") if Fixture(n).meta["F"] <= 512]
+
+
+@pytest.mark.parametrize("name", CHAINS)
+def test_chain_matches_reference_golden(name):
+    """diffusion_utils.p_sample_loop drop-in (injected noise) vs the reference's recorded trajectory."""
+    from nested_diffusion_b200 import diffusion_utils as du
+
+    fx = ChainFixture(name)
+    m = fx.meta
+    sd, x, yhat, noise, alphas, omabs = fx.materialize()
+    model = make_model(m, sd)
+    xg, yg, ng = x.cuda(), yhat.cuda(), noise.cuda()
+    ag, og = alphas.cuda(), omabs.cuda()
+    for prec in precisions_for(m["F"]):
+        with torch.no_grad():
+            seq = du.p_sample_loop(model, xg, yg, yg, m["T"], ag, og, only_last_sample=False, noise=ng, precision=prec)
+            y0 = du.p_sample_loop(model, xg, yg, yg, m["T"], ag, og, only_last_sample=True, noise=ng, precision=prec)
+        assert isinstance(seq, list) and len(seq) == m["T"] + 1
+        traj = torch.stack(seq).cpu()
+        assert torch.equal(traj[-1], y0.cpu()), "trajectory and only_last_sample runs must agree bitwise"
+        err = rel_err(traj[m["keep"]], fx["traj"])
+        assert err <= TOL[prec], f"{name}/{prec}: rel err {err:.3e}"
+        ok, n_safe = labels_match(y0.cpu(), fx["y0"], 4 * TOL[prec] * max(1.0, float(fx["y0"].abs().max())))
+        assert ok and n_safe > 0
+
+
+@pytest.mark.parametrize("name", [n for n in CHAINS if Fixture(n).meta["F"] > 128])
+def test_tensor_path_matches_operand_rounding_emulation(name):
+    """Tight check: the tensor-core chain vs the oracle's packed form with identically rounded operands."""
+    from nested_diffusion_b200 import diffusion_utils as du
+
+    fx = ChainFixture(name)
+    m = fx.meta
+    sd, x, yhat, noise, alphas, omabs = fx.materialize()
+    model = make_model(m, sd)
+    with torch.no_grad():
+        xf = orc.encoder_features(sd, x)
+    for prec in ("fp16", "bf16"):
+        with torch.no_grad():
+            emu = orc.packed_sample(sd, xf, yhat, yhat, m["T"], alphas, omabs, noise, operand_dtype=ODT[prec])
+            y0 = du.p_sample_loop(model, x.cuda(), yhat.cuda(), yhat.cuda(), m["T"], alphas.cuda(), omabs.cuda(),
+                                  only_last_sample=True, noise=noise.cuda(), precision=prec).cpu()
+        err = rel_err(y0, emu)
+        assert err <= TOL_EMU * (10 if prec == "bf16" else 1), f"{name}/{prec}: rel err vs emulation {err:.3e}"
+
+
+@pytest.mark.parametrize("F,rows,prec", [(256, 128, "fp16"), (256, 100, "bf16"), (512, 300, "fp16"), (1024, 257, "fp16")])
+def test_single_gemm_layer(F, rows, prec):
+    """ladine_debug_layer: one tcgen05 GEMM + fused epilogue vs torch FP64 on identically rounded operands."""
+    import ctypes as C
+
+    from nested_diffusion_b200 import _capi, engine
+
+    T, Cc = 4, 2
+    sd = orc.synth_state_dict(7, F, 16, 16, Cc, T)
+    pm = engine.PackedMember({k: v.cuda() for k, v in sd.items()}, n_steps=T, precision=prec)
+    p = orc.fold_member(sd, T, torch.float64)
+    dt = ODT[prec]
+    g = torch.Generator().manual_seed(1)
+    rows_pad = (rows + 127) // 128 * 128
+    h_in = torch.zeros(rows_pad, pm.Fp, dtype=dt)
+    h_in[:rows, :F] = (torch.rand(rows, F, generator=g) * 2).to(dt)
+    lib, h = _capi.load(), _capi.handle(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    t = 2
+    hin_g = h_in.cuda()
+    # layer 2
+    h_out = torch.zeros(rows_pad, pm.Fp, dtype=dt, device="cuda")
+    _capi.check(h, lib.ladine_debug_layer(h, pm.ptr, 2, t, hin_g.data_ptr(), rows, h_out.data_ptr(), None, stream))
+    torch.cuda.synchronize()
+    W2 = p["W2"].to(dt).double()
+    want = torch.nn.functional.softplus(p["A2"][t] * (h_in[:rows, :F].double() @ W2.T) + p["C2"][t])
+    got = h_out[:rows, :F].double().cpu()
+    ulp = 2.0 ** (-10 if prec == "fp16" else -7)
+    assert ((got - want).abs() <= ulp * want.abs() + 1e-6).all(), float(((got - want).abs() / (want.abs() + 1e-6)).max())
+    # layer 3 (+ fused lin4 partials)
+    NB = pm.Fp // 256
+    part = torch.zeros(rows_pad, NB, pm.Cp, device="cuda")
+    _capi.check(h, lib.ladine_debug_layer(h, pm.ptr, 3, t, hin_g.data_ptr(), rows, None, part.data_ptr(), stream))
+    torch.cuda.synchronize()
+    W3 = p["W3"].to(dt).double()
+    h3 = torch.nn.functional.softplus(p["A3"][t] * (h_in[:rows, :F].double() @ W3.T) + p["C3"][t])
+    want_eps = h3 @ p["W4"].T
+    got_eps = part[:rows, :, :Cc].double().sum(dim=1).cpu()
+    assert (got_eps - want_eps).abs().max() <= 2e-5 * max(1.0, float(want_eps.abs().max()))
+
+
+def test_philox_equals_injected_replay_and_is_deterministic():
+    """Philox stream == ladine_fill_noise replay (bitwise), run-to-run bitwise reproducible."""
+    import nested_diffusion_b200 as nd
+    from nested_diffusion_b200 import engine
+    from nested_diffusion_b200.schedule import coef_table
+
+    for F, prec in ((64, "fp32"), (256, "fp16")):
+        T, N, D, K, Cc = 25, 37, 3, 2, 2
+        sds = [orc.synth_state_dict(200 + k, F, 16, 16, Cc, T) for k in range(K)]
+        pms = [nd.PackedMember({k: v.cuda() for k, v in sd.items()}, n_steps=T, precision=prec) for sd in sds]
+        g = torch.Generator().manual_seed(3)
+        xf = torch.randn(K, N, F, generator=g).cuda()
+        yh = torch.softmax(torch.randn(K, N, Cc, generator=g), -1).cuda()
+        alphas, omabs = orc.schedule_tensors(orc.make_beta_schedule("linear", T, 1e-4, 0.02))
+        coef = coef_table(alphas, omabs, T)
+        a = engine.sample_chains(pms, xf, yh, yh, coef, D, seed=1234)["y"]
+        b = engine.sample_chains(pms, xf, yh, yh, coef, D, seed=1234)["y"]
+        c = engine.sample_chains(pms, xf, yh, yh, coef, D, seed=1235)["y"]
+        noise = engine.fill_noise("cuda", K, N, D, Cc, T, 1234)
+        d = engine.sample_chains(pms, xf, yh, yh, coef, D, noise=noise)["y"]
+        assert torch.equal(a, b) and torch.equal(a, d) and not torch.equal(a, c)
+        z = noise.flatten().double()
+        assert abs(float(z.mean())) < 0.05 and abs(float(z.std()) - 1) < 0.05
+
+
+def test_partition_invariance_over_image_tiles():
+    """Sharding rows by image tile with global Philox ids reproduces the unsharded result bitwise (§8e)."""
+    import nested_diffusion_b200 as nd
+    from nested_diffusion_b200 import engine
+    from nested_diffusion_b200.schedule import coef_table
+
+    for F, prec in ((64, "fp32"), (256, "fp16")):
+        T, N, D, K, Cc = 20, 50, 4, 3, 2
+        sds = [orc.synth_state_dict(300 + k, F, 16, 16, Cc, T) for k in range(K)]
+        pms = [nd.PackedMember({k: v.cuda() for k, v in sd.items()}, n_steps=T, precision=prec) for sd in sds]
+        g = torch.Generator().manual_seed(4)
+        xf = torch.randn(K, N, F, generator=g).cuda()
+        yh = torch.softmax(torch.randn(K, N, Cc, generator=g), -1).cuda()
+        alphas, omabs = orc.schedule_tensors(orc.make_beta_schedule("linear", T, 1e-4, 0.02))
+        coef = coef_table(alphas, omabs, T)
+        full = engine.sample_chains(pms, xf, yh, yh, coef, D, seed=77, member_ids=[5, 6, 7])["y"]
+        parts = []
+        for r in range(3):
+            lo, hi = nd.shard_bounds(N, r, 3)
+            parts.append(engine.sample_chains(pms, xf[:, lo:hi], yh[:, lo:hi], yh[:, lo:hi], coef, D, seed=77,
+                                              member_ids=[5, 6, 7], image_offset=lo, images_total=N)["y"])
+        assert torch.equal(full, torch.cat(parts, dim=2))
+        # member split as well: members 1..2 alone give the same chains
+        sub = engine.sample_chains(pms[1:], xf[1:], yh[1:], yh[1:], coef, D, seed=77, member_ids=[6, 7])["y"]
+        assert torch.equal(full[1:], sub)
+
+
+@pytest.mark.parametrize("name", names("ensemble"))
+def test_nested_ensemble_matches_reference_loop(name):
+    """NestedEnsemble.sample (one batched call) vs the reference's K x D sequential p_sample_loop calls."""
+    import nested_diffusion_b200 as nd
+
+    fx = EnsembleFixture(name)
+    m = fx.meta
+    sds, x, y0hats, noise, alphas, omabs = fx.materialize()
+    models = [make_model(m, sd) for sd in sds]
+    for prec in precisions_for(m["F"]):
+        ens = nd.NestedEnsemble(models, precision=prec)
+        with torch.no_grad():
+            res = ens.sample(x.cuda(), [y.cuda() for y in y0hats], m["D"], m["T"], alphas.cuda(), omabs.cuda(),
+                             noise=noise.cuda(), temperature=0.1737)
+        y0 = res.y0.cpu()
+        assert y0.shape == fx["y0"].shape
+        assert rel_err(y0, fx["y0"]) <= TOL[prec]
+        want_p = orc.convert_to_prob(y0, 0.1737)
+        assert torch.allclose(res.probs.cpu(), want_p, atol=2e-6)
+
+
+def test_single_step_entry_points():
+    """p_sample and p_sample_t_1to0 drop-ins vs the oracle on one step."""
+    from nested_diffusion_b200 import diffusion_utils as du
+
+    fx = ChainFixture("small_f128_t50")
+    m = fx.meta
+    sd, x, yhat, noise, alphas, omabs = fx.materialize()
+    model = make_model(m, sd)
+    eps_fn = orc._Eps(sd, x, hoist=True)
+    y = yhat + noise[0]
+    with torch.no_grad():
+        for t in (49, 17, 1):
+            want = orc.p_sample(eps_fn, y, yhat, yhat, t, alphas, omabs, noise[1])
+            got = du.p_sample(model, x.cuda(), y.cuda(), yhat.cuda(), yhat.cuda(), t, alphas.cuda(), omabs.cuda(),
+                              noise=noise[1].cuda()).cpu()
+            assert rel_err(got, want) <= TOL["fp32"]
+        want = orc.p_sample_t_1to0(eps_fn, y, yhat, yhat, omabs)
+        got = du.p_sample_t_1to0(model, x.cuda(), y.cuda(), yhat.cuda(), yhat.cuda(), omabs.cuda()).cpu()
+        assert rel_err(got, want) <= TOL["fp32"]
+
+
+def test_error_behaviour():
+    from nested_diffusion_b200 import diffusion_utils as du
+
+    fx = ChainFixture("small_f128_t50")
+    m = fx.meta
+    sd, x, yhat, noise, alphas, omabs = fx.materialize()
+    cpu_model = make_model(m, sd, device="cpu")
+    with pytest.raises(RuntimeError):
+        du.p_sample_loop(cpu_model, x, yhat, yhat, m["T"], alphas, omabs, only_last_sample=True)
+    model = make_model(m, sd)
+    with pytest.raises(NotImplementedError):
+        du.p_sample_loop(model.train(), x.cuda(), yhat.cuda(), yhat.cuda(), m["T"], alphas, omabs)
+    model.eval()
+    with pytest.raises(NotImplementedError):
+        du.p_sample_loop(model, x.cuda(), yhat.cuda(), yhat.cuda(), m["T"], alphas, omabs, output_detach=False)
+    with pytest.raises(ValueError):
+        du.p_sample_loop(model, x.cuda(), yhat.cuda()[:3], yhat.cuda(), m["T"], alphas, omabs)
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("name", [n for n in names("chain") if Fixture(n).meta["F"] == 4096])
+def test_shipped_trunk_width_full_chain(name):
+    """F = 4096 (the shipped feature_dim), T = 1000, B = 64: reference golden vs FP16 and BF16 chains."""
+    from nested_diffusion_b200 import diffusion_utils as du
+
+    fx = ChainFixture(name)
+    m = fx.meta
+    sd, x, yhat, noise, alphas, omabs = fx.materialize()
+    model = make_model(m, sd)
+    for prec in ("fp16", "bf16"):
+        with torch.no_grad():
+            seq = du.p_sample_loop(model, x.cuda(), yhat.cuda(), yhat.cuda(), m["T"], alphas.cuda(), omabs.cuda(),
+                                   only_last_sample=False, noise=noise.cuda(), precision=prec)
+        traj = torch.stack(seq).cpu()
+        err = rel_err(traj[m["keep"]], fx["traj"])
+        print(f"{name}/{prec}: rel err {err:.3e}, |y0|max {float(fx['y0'].abs().max()):.3e}")
+        assert err <= TOL[prec]
+        ok, n_safe = labels_match(traj[-1], fx["y0"], 4 * TOL[prec] * max(1.0, float(fx["y0"].abs().max())))
+        assert ok and n_safe > 0
