@@ -110,7 +110,7 @@ typedef struct {
   int32_t draw_offset;      /* global index of draw 0 of this call                       */
   int32_t draws_total;      /* global draw count; 0 means D                              */
   float* y_out;             /* [K, D, N, C]  y after step t_last                         */
-  float* traj_out;          /* [K, D, S+1?, N, C] or NULL: every y (y_T first) -- only_last_sample=False */
+  float* traj_out;          /* [K, D, n_traj, N, C] or NULL: every y in order (y_T first when drawn here); n_traj = (y_init?0:1) + #steps */
   float* prob_out;          /* [K, D, N, C] or NULL: softmax(-(y-1)^2 / temperature) (classification_train_separately.py:392-398) */
   float temperature;        /* used only when prob_out != NULL                           */
   void* stream;             /* cudaStream_t                                              */
@@ -142,6 +142,13 @@ int ladine_fill_noise(ladine_handle* h, const ladine_sample_args* args, int32_t 
  * and current workspace bytes. */
 int64_t ladine_last_launches(const ladine_handle* h);
 uint64_t ladine_workspace_bytes(const ladine_handle* h);
+
+/* Optional per-kernel timing of the tensor-core path.  When enabled, ladine_sample brackets every
+ * GEMM / tail-head launch with CUDA events on the caller's stream; ladine_get_profile synchronises
+ * those events and returns, per kernel family {0: gemm layer 2, 1: gemm layer 3, 2: tail/head},
+ * the summed device time in milliseconds and the launch count since the last call, then resets. */
+int ladine_set_profiling(ladine_handle* h, int enabled);
+int ladine_get_profile(ladine_handle* h, float ms_out[3], int64_t count_out[3]);
 
 /* Debug/test entry: one trunk GEMM layer (2 or 3) of `member` at table index t on `rows` rows.
  * h_in  : [rows_pad, Fpad] 16-bit operands in the member's operand type (rows_pad = rows rounded up to 128)

@@ -254,6 +254,11 @@ int ladine_destroy(ladine_handle* h) {
       cudaDeviceSynchronize();
       cudaFree(h->ws);
     }
+    for (auto& s : h->spans) {
+      cudaEventDestroy(s.a);
+      cudaEventDestroy(s.b);
+    }
+    for (auto e : h->pool) cudaEventDestroy(e);
   }
   delete h;
   return LADINE_OK;
@@ -505,6 +510,33 @@ int ladine_fill_noise(ladine_handle* h, const ladine_sample_args* a, int32_t num
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(h, e, "noise fill kernel");
+  return LADINE_OK;
+}
+
+int ladine_set_profiling(ladine_handle* h, int enabled) {
+  if (!h) return LADINE_ERR_INVALID;
+  h->profiling = enabled != 0;
+  return LADINE_OK;
+}
+
+int ladine_get_profile(ladine_handle* h, float ms_out[3], int64_t count_out[3]) {
+  if (!h || !ms_out || !count_out) return LADINE_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  for (int i = 0; i < 3; ++i) {
+    ms_out[i] = 0.f;
+    count_out[i] = 0;
+  }
+  for (auto& s : h->spans) {
+    cudaError_t e = cudaEventSynchronize(s.b);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, s.a, s.b);
+    if (e != cudaSuccess) return fail_cuda(h, e, "profile event readback");
+    ms_out[s.kind] += ms;
+    count_out[s.kind] += 1;
+    h->pool.push_back(s.a);
+    h->pool.push_back(s.b);
+  }
+  h->spans.clear();
   return LADINE_OK;
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <vector>
 
 #include "ladine_common.cuh"
 
@@ -43,6 +44,11 @@ struct ladine_handle {
   uint64_t ws_bytes = 0;
   // driver entry point for tensor-map encoding (resolved lazily through the runtime)
   void* encode_tiled = nullptr;
+  // optional per-kernel event timing (tensor path)
+  bool profiling = false;
+  struct Span { cudaEvent_t a, b; int kind; };
+  std::vector<Span> spans;       // recorded since the last ladine_get_profile
+  std::vector<cudaEvent_t> pool; // reusable events
 };
 
 namespace ladine {

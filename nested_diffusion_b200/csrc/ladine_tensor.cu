@@ -599,6 +599,34 @@ cudaError_t launch_tail(const TailHeadParams& p, dim3 grid, bool bf16, int Cp, c
   return cudaGetLastError();
 }
 
+struct ProfSpan {
+  ladine_handle* h;
+  cudaStream_t st;
+  cudaEvent_t a = nullptr;
+  int kind;
+  ProfSpan(ladine_handle* h_, cudaStream_t st_, int kind_) : h(h_), st(st_), kind(kind_) {
+    if (!h->profiling) return;
+    a = take();
+    cudaEventRecord(a, st);
+  }
+  ~ProfSpan() {
+    if (!a) return;
+    cudaEvent_t b = take();
+    cudaEventRecord(b, st);
+    h->spans.push_back({a, b, kind});
+  }
+  cudaEvent_t take() {
+    cudaEvent_t e;
+    if (!h->pool.empty()) {
+      e = h->pool.back();
+      h->pool.pop_back();
+    } else {
+      cudaEventCreate(&e);
+    }
+    return e;
+  }
+};
+
 }  // namespace
 
 size_t tensor_gemm_smem_bytes(int Cp) {
@@ -696,9 +724,15 @@ cudaError_t launch_tensor_chain(ladine_handle* h, const ladine_member* const* me
       g3.scale[k] = members[k]->A[2] + (size_t)t * Fp;
       g3.shift[k] = members[k]->Cc[2] + (size_t)t * Fp;
     }
-    e = launch_gemm<2>(g2, grid, bf16, Cp, st);
+    {
+      ProfSpan ps(h, st, 0);
+      e = launch_gemm<2>(g2, grid, bf16, Cp, st);
+    }
     if (e != cudaSuccess) return e;
-    e = launch_gemm<3>(g3, grid, bf16, Cp, st);
+    {
+      ProfSpan ps(h, st, 1);
+      e = launch_gemm<3>(g3, grid, bf16, Cp, st);
+    }
     if (e != cudaSuccess) return e;
     tp.coef = h_coef[t];
     tp.t = t;
@@ -706,11 +740,14 @@ cudaError_t launch_tensor_chain(ladine_handle* h, const ladine_member* const* me
     tp.traj_entry = slot_base + (a.t_first - t);
     const bool last = (t == a.t_last);
     tp.write_out = last ? 1 : 0;
-    if (last) {
-      e = launch_tail<kFinal>(tp, tgrid, bf16, Cp, st);
-    } else {
-      set_head_rows(t - 1);
-      e = launch_tail<kMid>(tp, tgrid, bf16, Cp, st);
+    {
+      ProfSpan ps(h, st, 2);
+      if (last) {
+        e = launch_tail<kFinal>(tp, tgrid, bf16, Cp, st);
+      } else {
+        set_head_rows(t - 1);
+        e = launch_tail<kMid>(tp, tgrid, bf16, Cp, st);
+      }
     }
     if (e != cudaSuccess) return e;
     *launches += 3;

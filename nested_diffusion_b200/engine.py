@@ -262,3 +262,17 @@ def fill_noise(device, K, N, D, C_cls, T, seed, *, t_first=None, t_last=0, has_i
         a.stream = torch.cuda.current_stream().cuda_stream
         _capi.check(h, lib.ladine_fill_noise(h, C.byref(a), C_cls, C.c_void_p(out.data_ptr())))
     return out
+
+
+def set_profiling(device_index: int, enabled: bool) -> None:
+    """Bracket every tensor-path kernel launch with CUDA events (see ladine_get_profile)."""
+    _capi.check(_capi.handle(device_index), _capi.load().ladine_set_profiling(_capi.handle(device_index), int(enabled)))
+
+
+def get_profile(device_index: int) -> dict:
+    """{'gemm2': (ms, launches), 'gemm3': (...), 'tailhead': (...)} since the last call (synchronises)."""
+    ms = (C.c_float * 3)()
+    cnt = (C.c_int64 * 3)()
+    h = _capi.handle(device_index)
+    _capi.check(h, _capi.load().ladine_get_profile(h, ms, cnt))
+    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("gemm2", "gemm3", "tailhead"))}
