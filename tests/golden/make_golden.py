@@ -164,8 +164,31 @@ def schedules_fixture(name="schedules"):
     save(name, dict(kind="schedules", start=1e-4, end=0.02), **arrays)
 
 
+def layout_fixture(name="state_dict_layout"):
+    """Key names, shapes and dtypes of the reference ConditionalModel.state_dict() (the checkpoint
+    contract, latent_model.py:108-167) plus one forward pass for a forward-parity check."""
+    arrays, layouts = {}, {}
+    for tag, guidance, C in (("guid_c2", True, 2), ("noguid_c3", False, 3)):
+        F, H, Dx, T = 8, 6, 10, 5
+        torch.manual_seed(7)
+        m = ref_lm.ConditionalModel(ref_config(F, H, Dx, C, T), guidance=guidance).eval()
+        layouts[tag] = {k: [list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()}
+        g = torch.Generator().manual_seed(8)
+        x = torch.rand(4, Dx, generator=g)
+        y = torch.randn(4, C, generator=g)
+        yh = torch.softmax(torch.randn(4, C, generator=g), 1)
+        t = torch.tensor([3])
+        with torch.no_grad():
+            out = m(x, y, t, yh)
+        for k, v in m.state_dict().items():
+            arrays[f"{tag}/sd/{k}"] = v
+        arrays.update({f"{tag}/x": x, f"{tag}/y": y, f"{tag}/yh": yh, f"{tag}/out": out})
+    save(name, dict(kind="layout", F=8, H=6, Dx=10, T=5, layouts=layouts), **arrays)
+
+
 FIXTURES = {
     "schedules": schedules_fixture,
+    "layout": layout_fixture,
     # tiny, inputs stored verbatim, full trajectory
     "small": lambda: chain_fixture("small_f128_t50", F=128, H=64, Dx=256, C=2, T=50, B=64, sd_seed=11,
                                    in_seed=12, noise_seed=13, store_inputs=True),

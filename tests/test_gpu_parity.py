@@ -159,6 +159,19 @@ def test_philox_equals_injected_replay_and_is_deterministic():
         assert abs(float(z.mean())) < 0.05 and abs(float(z.std()) - 1) < 0.05
 
 
+def test_device_philox_matches_numpy_oracle():
+    """ladine_fill_noise vs the NumPy restatement of Philox4x32-10 + Box-Muller (KAT-pinned on the CPU side)."""
+    from nested_diffusion_b200 import engine
+    from oracle import philox_oracle as pho
+
+    got = engine.fill_noise("cuda", 2, 9, 3, 3, 6, 99, member_ids=[4, 9], image_offset=5, images_total=20,
+                            draw_offset=1, draws_total=7).cpu().double().numpy()
+    want = pho.noise_tensor(99, 2, 3, 6, 9, 3, member_ids=[4, 9], image_offset=5, images_total=20, draw_offset=1,
+                            draws_total=7)
+    assert got.shape == want.shape
+    assert abs(got - want).max() < 5e-6
+
+
 def test_partition_invariance_over_image_tiles():
     """Sharding rows by image tile with global Philox ids reproduces the unsharded result bitwise (§8e)."""
     import nested_diffusion_b200 as nd

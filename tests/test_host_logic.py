@@ -1,0 +1,251 @@
+"""CPU-only tests: host logic, C-ABI surface, statistics, sharding/gather over gloo, Philox oracle."""
+import argparse
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import nested_diffusion_b200 as nd
+from nested_diffusion_b200 import _capi, schedule, stats
+from oracle import ladine_oracle as orc
+from oracle import philox_oracle as pho
+from tests.golden_util import Fixture
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ C ABI surface
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ladine.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ladine_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _capi.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"libladine.so lacks {name} declared in include/ladine.h"
+    assert sorted(_capi.SYMBOLS) == declared, "ctypes binding and header disagree"
+    assert lib.ladine_version() == 1
+
+
+def test_struct_sizes_match_header_layout():
+    # sizes the C side checks through struct_size: any drift is an error at call time, not corruption
+    assert ctypes.sizeof(_capi.MemberDesc) == 8 * 4 + 8 * 8 + 15 * 8
+    assert ctypes.sizeof(_capi.SampleArgs) % 8 == 0
+
+
+def test_create_fails_cleanly_without_a_device():
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    out = ctypes.c_void_p()
+    rc = _capi.load().ladine_create(0, ctypes.byref(out))
+    assert rc < 0 and not out.value
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "nested_diffusion_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_no_cpu_fallback():
+    fx = Fixture("state_dict_layout")
+    cfg = argparse.Namespace(diffusion=argparse.Namespace(timesteps=5),
+                             data=argparse.Namespace(num_classes=2, dataset="ChestXRay"),
+                             model=argparse.Namespace(data_dim=10, arch="linear", feature_dim=8, hidden_dim=6))
+    m = nd.ConditionalModel(cfg, guidance=True).eval()
+    a, o = schedule.schedule_tensors(schedule.make_beta_schedule("linear", 5, 1e-4, 0.02))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        nd.diffusion_utils.p_sample_loop(m, fx["guid_c2/x"], fx["guid_c2/yh"], fx["guid_c2/yh"], 5, a, o)
+
+
+# ------------------------------------------------------------------ drop-in module layout
+@pytest.mark.parametrize("tag,guidance,C", [("guid_c2", True, 2), ("noguid_c3", False, 3)])
+def test_conditional_model_matches_reference_layout_and_forward(tag, guidance, C):
+    fx = Fixture("state_dict_layout")
+    m = fx.meta
+    cfg = argparse.Namespace(diffusion=argparse.Namespace(timesteps=m["T"]),
+                             data=argparse.Namespace(num_classes=C, dataset="ChestXRay"),
+                             model=argparse.Namespace(data_dim=m["Dx"], arch="linear", feature_dim=m["F"],
+                                                      hidden_dim=m["H"]))
+    model = nd.ConditionalModel(cfg, guidance=guidance).eval()
+    mine = {k: [list(v.shape), str(v.dtype)] for k, v in model.state_dict().items()}
+    assert mine == m["layouts"][tag], "state_dict layout differs from the reference (checkpoint contract)"
+    sd = {k[len(tag) + 4:]: v for k, v in fx.arrays.items() if k.startswith(tag + "/sd/")}
+    model.load_state_dict(sd)  # strict
+    with torch.no_grad():
+        out = model(fx[f"{tag}/x"], fx[f"{tag}/y"], torch.tensor([3]), fx[f"{tag}/yh"])
+        out_o = orc.denoiser_forward(sd, fx[f"{tag}/x"], fx[f"{tag}/y"], torch.tensor([3]), fx[f"{tag}/yh"])
+    assert torch.allclose(out, fx[f"{tag}/out"], rtol=1e-6, atol=1e-7)
+    assert torch.allclose(out_o, fx[f"{tag}/out"], rtol=1e-6, atol=1e-7)
+
+
+def test_drop_in_module_surface():
+    du = nd.diffusion_utils
+    for name in ("make_beta_schedule", "extract", "q_sample", "p_sample", "p_sample_t_1to0", "y_0_reparam",
+                 "p_sample_loop"):
+        assert callable(getattr(du, name))
+    import inspect
+
+    sig = inspect.signature(du.p_sample_loop)
+    assert list(sig.parameters)[:10] == ["model", "x", "y_0_hat", "y_T_mean", "n_steps", "alphas",
+                                         "one_minus_alphas_bar_sqrt", "only_last_sample",
+                                         "input_model_original_version", "output_detach"]
+    assert sig.parameters["only_last_sample"].default is False
+    assert list(inspect.signature(du.p_sample).parameters)[:9] == [
+        "model", "x", "y", "y_0_hat", "y_T_mean", "t", "alphas", "one_minus_alphas_bar_sqrt", "output_detach"]
+
+
+# ------------------------------------------------------------------ schedules / coefficients
+def test_schedules_and_coef_table_equal_oracle_bitwise():
+    fx = Fixture("schedules")
+    for key, ref in fx.arrays.items():
+        kind, T = key.split("/")
+        got = schedule.make_beta_schedule(kind, int(T), fx.meta["start"], fx.meta["end"]).float()
+        assert torch.allclose(got, ref, rtol=1e-6, atol=0), key
+    for kind in ("linear", "cosine", "quad"):
+        betas = schedule.make_beta_schedule(kind, 1000, 1e-4, 0.02)
+        a, o = schedule.schedule_tensors(betas, kind)
+        a2, o2 = orc.schedule_tensors(betas, kind)
+        assert torch.equal(a, a2) and torch.equal(o, o2)
+        assert torch.equal(schedule.coef_table(a, o, 1000), orc.coef_table(a, o, 1000))
+        assert torch.equal(schedule.coef_table(a, o, 100), orc.coef_table(a, o, 100))
+
+
+def test_coef_table_reproduces_reference_step_scalars():
+    """row t of the table == the scalars diffusion_utils.p_sample computes at that t (same torch expressions)."""
+    a, o = schedule.schedule_tensors(schedule.make_beta_schedule("linear", 50, 1e-4, 0.02))
+    tab = schedule.coef_table(a, o, 50)
+    y = torch.zeros(1, 2)
+    for t in (49, 7, 1):
+        tt = torch.tensor([t])
+        alpha_t, s_t, s_p = orc.extract(a, tt, y), orc.extract(o, tt, y), orc.extract(o, tt - 1, y)
+        q, qp = (1 - s_t.square()).sqrt(), (1 - s_p.square()).sqrt()
+        g0 = (1 - alpha_t) * qp / s_t.square()
+        g1 = s_p.square() * alpha_t.sqrt() / s_t.square()
+        g2 = 1 + (q - 1) * (alpha_t.sqrt() + qp) / s_t.square()
+        sig = (s_p.square() / s_t.square() * (1 - alpha_t)).sqrt()
+        want = torch.stack([(1 / q), 1 - q, s_t, g0, g1, g2, sig]).flatten()
+        assert torch.equal(tab[t, :7], want)
+
+
+# ------------------------------------------------------------------ statistics
+def test_statistics_match_restated_reference():
+    g = torch.Generator().manual_seed(0)
+    S, N, C = 100, 57, 2
+    samples = torch.randn(S, N, C, generator=g) * 0.7 + torch.tensor([0.3, 0.6])
+    label = torch.randint(0, C, (N,), generator=g)
+    mv = stats.majority_voting_for_mc_samples(samples)
+    assert torch.equal(mv, orc.majority_vote(samples))
+    assert torch.equal(stats.majority_voting_for_mc_samples(list(samples)), mv)
+    temp = 0.1737
+    conf = stats.compute_ensemble_confidence(samples, temp)
+    assert torch.allclose(conf, orc.ensemble_confidence(samples, temp), atol=1e-7)
+    assert torch.allclose(stats.compute_ece(conf, label), orc.ece_l1(conf, label), atol=1e-7)
+    for mine, ref in zip(stats.compute_mean_piws_for_class(samples, mv, label),
+                         orc.mean_piw_per_class(samples, mv, label)):
+        assert torch.allclose(mine, ref, equal_nan=True)
+    for mine, ref in zip(stats.calculate_variances(samples, mv, label), orc.class_variances(samples, mv, label)):
+        assert torch.allclose(mine, ref)
+    assert float(stats.compute_accuracy(mv, label)) == pytest.approx(float((mv == label).float().mean()))
+
+
+def test_majority_vote_ties_go_to_smallest_label():
+    # 4 chains, 2 vote class 1 and 2 vote class 0 -> the reference returns 0 (sorted unique + first argmax)
+    s = torch.tensor([[[0.0, 1.0]], [[0.0, 1.0]], [[1.0, 0.0]], [[1.0, 0.0]]])
+    assert int(stats.majority_voting_for_mc_samples(s)[0]) == 0 == int(orc.majority_vote(s)[0])
+    s3 = torch.zeros(6, 1, 3)
+    for i, c in enumerate([2, 2, 1, 1, 0, 2]):
+        s3[i, 0, c] = 1
+    assert int(stats.majority_voting_for_mc_samples(s3)[0]) == 2
+
+
+def test_ece_known_answer():
+    probs = torch.tensor([[0.9, 0.1], [0.8, 0.2], [0.4, 0.6], [0.55, 0.45]])
+    target = torch.tensor([0, 1, 1, 0])
+    # bins (0.5,0.6]: conf .55 acc 1 -> wait .6 falls in (0.5,0.6]: two items conf (.6,.55) acc (1,1);
+    # (0.7,0.8]: conf .8 acc 0; (0.8,0.9]: conf .9 acc 1
+    want = (abs(1 - 0.575) * 2 + abs(0 - 0.8) + abs(1 - 0.9)) / 4
+    assert float(stats.compute_ece(probs, target)) == pytest.approx(want, abs=1e-6)
+    assert float(orc.ece_l1(probs, target)) == pytest.approx(want, abs=1e-6)
+
+
+# ------------------------------------------------------------------ sharding + gather (gloo, 2 ranks)
+def test_shard_bounds_partition():
+    for n in (1, 7, 70, 71, 1024):
+        for w in (1, 2, 3, 8):
+            spans = [nd.shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import nested_diffusion_b200 as nd
+from nested_diffusion_b200 import stats
+rank, world, n = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=sys.argv[5])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+g = torch.Generator().manual_seed(5)
+full = torch.randn(n, 100, 2, generator=g)           # [N, K*D, C] "samples" every rank could have produced
+lo, hi = nd.shard_bounds(n, rank, world)
+got = nd.gather_image_shards(full[lo:hi].contiguous(), n)
+assert torch.equal(got, full), "gathered tensor differs from the unsharded one"
+mv = stats.majority_voting_for_mc_samples(got.permute(1, 0, 2))
+ref = stats.majority_voting_for_mc_samples(full.permute(1, 0, 2))
+assert torch.equal(mv, ref)
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+@pytest.mark.parametrize("n_images", [70, 7])
+def test_gather_image_shards_two_ranks_gloo(n_images, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + (os.getpid() + n_images) % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(r), "2", str(n_images), port],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{o}"
+        assert f"rank {r} ok" in o
+
+
+# ------------------------------------------------------------------ Philox oracle
+def test_philox_known_answer_vectors():
+    """Random123 kat_vectors for philox4x32-10."""
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+        ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+    ]
+    for ctr, key, want in kat:
+        got = pho.philox4x32_10(np.array(ctr, dtype=np.uint32), np.array(key, dtype=np.uint32))
+        assert [int(v) for v in got] == want
+
+
+def test_philox_noise_is_standard_normal_and_partition_invariant():
+    z = pho.noise_tensor(1234, K=2, D=3, S=50, N=40, C=2)
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1) < 0.02
+    # kurtosis of a normal is 3
+    assert abs(((z - z.mean()) ** 4).mean() / z.var() ** 2 - 3) < 0.15
+    part = pho.noise_tensor(1234, K=2, D=3, S=50, N=15, C=2, image_offset=25, images_total=40)
+    assert np.array_equal(part, z[:, :, :, 25:40])
+    member1 = pho.noise_tensor(1234, K=1, D=3, S=50, N=40, C=2, member_ids=[1])
+    assert np.array_equal(member1[0], z[1])
