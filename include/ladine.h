@@ -143,12 +143,19 @@ int ladine_fill_noise(ladine_handle* h, const ladine_sample_args* args, int32_t 
 int64_t ladine_last_launches(const ladine_handle* h);
 uint64_t ladine_workspace_bytes(const ladine_handle* h);
 
+/* Tuning knobs.  "lanes" (1..4, default 2): how many groups of members the tensor-core path advances
+ * concurrently on internal streams (forked from / joined to the caller's stream), so one group's
+ * tail/head kernel and kernel boundaries hide under another group's GEMMs. */
+int ladine_set_option(ladine_handle* h, const char* key, int64_t value);
+
 /* Optional per-kernel timing of the tensor-core path.  When enabled, ladine_sample brackets every
  * GEMM / tail-head launch with CUDA events on the caller's stream; ladine_get_profile synchronises
  * those events and returns, per kernel family {0: gemm layer 2, 1: gemm layer 3, 2: tail/head},
- * the summed device time in milliseconds and the launch count since the last call, then resets. */
+ * the summed device time in milliseconds and the launch count since the last call, then resets.
+ * ms_out[3] is the union of the GEMM spans (wall time during which at least one GEMM launch was in
+ * flight; equals ms_out[0] + ms_out[1] with one lane). */
 int ladine_set_profiling(ladine_handle* h, int enabled);
-int ladine_get_profile(ladine_handle* h, float ms_out[3], int64_t count_out[3]);
+int ladine_get_profile(ladine_handle* h, float ms_out[4], int64_t count_out[3]);
 
 /* Debug/test entry: one trunk GEMM layer (2 or 3) of `member` at table index t on `rows` rows.
  * h_in  : [rows_pad, Fpad] 16-bit operands in the member's operand type (rows_pad = rows rounded up to 128)

@@ -1,5 +1,6 @@
 // C ABI of libladine (include/ladine.h): handle/member lifetime, member packing (fold + re-layout),
 // and the dispatcher of the hot path.  No torch types, no exceptions across the boundary.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -259,6 +260,11 @@ int ladine_destroy(ladine_handle* h) {
       cudaEventDestroy(s.b);
     }
     for (auto e : h->pool) cudaEventDestroy(e);
+    for (int l = 1; l < ladine_handle::kMaxLanes; ++l) {
+      if (h->lane_stream[l]) cudaStreamDestroy(h->lane_stream[l]);
+      if (h->ev_join[l]) cudaEventDestroy(h->ev_join[l]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   }
   delete h;
   return LADINE_OK;
@@ -397,6 +403,32 @@ static int validate_sample(ladine_handle* h, const ladine_member* const* members
   return LADINE_OK;
 }
 
+// member groups: sizes differ by at most one, each <= LADINE_MAX_GROUP, at least `lanes` of them when K allows
+static std::vector<std::pair<int, int>> plan_groups(int K, int lanes) {
+  int n = (K + LADINE_MAX_GROUP - 1) / LADINE_MAX_GROUP;
+  const int want = lanes < K ? lanes : K;
+  if (n < want) n = want;
+  std::vector<std::pair<int, int>> g;
+  int k0 = 0;
+  for (int i = 0; i < n; ++i) {
+    const int kn = K / n + (i < K % n ? 1 : 0);
+    g.push_back({k0, kn});
+    k0 += kn;
+  }
+  return g;
+}
+
+static int ensure_lane_resources(ladine_handle* h, int lanes) {
+  cudaError_t e = cudaSuccess;
+  if (!h->ev_fork) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  for (int l = 1; l < lanes && e == cudaSuccess; ++l) {
+    if (!h->lane_stream[l]) e = cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking);
+    if (e == cudaSuccess && !h->ev_join[l]) e = cudaEventCreateWithFlags(&h->ev_join[l], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) return fail_cuda(h, e, "lane stream/event creation");
+  return LADINE_OK;
+}
+
 int ladine_sample(ladine_handle* h, const ladine_member* const* members, const ladine_sample_args* a) {
   if (!h) return LADINE_ERR_INVALID;
   int rc = validate_sample(h, members, a);
@@ -412,22 +444,34 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
   const StepCoef* h_coef = reinterpret_cast<const StepCoef*>(a->coef);
   static_assert(sizeof(StepCoef) == 8 * sizeof(float), "coef rows are 8 floats");
 
-  // workspace: sized for one launch group
-  const int G = a->K < LADINE_MAX_GROUP ? a->K : LADINE_MAX_GROUP;
+  // Tensor path: member groups advance concurrently on up to `lanes` streams (lane 0 = caller's stream).
+  // The resident path is a single launch per group and needs no lanes.
+  int lanes = tensor ? h->lanes : 1;
+  if (lanes < 1) lanes = 1;
+  if (lanes > ladine_handle::kMaxLanes) lanes = ladine_handle::kMaxLanes;
+  const std::vector<std::pair<int, int>> groups = plan_groups(a->K, lanes);
+  if ((int)groups.size() < lanes) lanes = (int)groups.size();
+  int gmax = 0;
+  for (auto& g : groups) gmax = g.second > gmax ? g.second : gmax;
+
+  // workspace: a coefficient table + one slice per lane, each sized for the largest group
   const int rows = a->N * a->D;
-  const int rows_pad = (rows + 127) / 128 * 128;
-  const uint64_t m_total = (uint64_t)G * rows_pad;
+  const int rows_pad = (rows + 255) / 256 * 256;  // covers both tile geometries (128- and 256-row tiles)
+  const uint64_t m_total = (uint64_t)gmax * rows_pad;
   uint64_t off = 0;
   const uint64_t o_coef = off; off = align_up(off + (uint64_t)a->T * sizeof(StepCoef), 1024);
-  const uint64_t o_u = off; off = align_up(off + (uint64_t)G * a->N * Fp * 4, 1024);
+  const uint64_t lane_base = off;
+  uint64_t lo = 0;
+  const uint64_t o_u = lo; lo = align_up(lo + (uint64_t)gmax * a->N * Fp * 4, 1024);
   uint64_t o_h1 = 0, o_h2 = 0, o_part = 0, o_y = 0;
   if (tensor) {
-    o_h1 = off; off = align_up(off + m_total * Fp * 2, 1024);
-    o_h2 = off; off = align_up(off + m_total * Fp * 2, 1024);
-    o_part = off; off = align_up(off + m_total * (Fp / 256) * Cp * 4, 1024);
-    o_y = off; off = align_up(off + m_total * Cp * 4, 1024);
+    o_h1 = lo; lo = align_up(lo + m_total * Fp * 2, 1024);
+    o_h2 = lo; lo = align_up(lo + m_total * Fp * 2, 1024);
+    o_part = lo; lo = align_up(lo + m_total * (Fp / 256) * Cp * 4, 1024);
+    o_y = lo; lo = align_up(lo + 2 * m_total * Cp * 4, 1024);
   }
-  rc = ensure_workspace(h, off);
+  const uint64_t lane_bytes = lo;
+  rc = ensure_workspace(h, lane_base + lane_bytes * lanes);
   if (rc != LADINE_OK) return rc;
   uint8_t* ws = static_cast<uint8_t*>(h->ws);
   cudaError_t e;
@@ -438,9 +482,15 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
     e = cudaMemcpyAsync(ws + o_coef, a->coef, (size_t)a->T * sizeof(StepCoef), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return fail_cuda(h, e, "coefficient upload");
   }
+  if (lanes > 1) {
+    rc = ensure_lane_resources(h, lanes);
+    if (rc != LADINE_OK) return rc;
+    e = cudaEventRecord(h->ev_fork, st);  // lanes start after everything already queued on the caller's stream
+    for (int l = 1; l < lanes && e == cudaSuccess; ++l) e = cudaStreamWaitEvent(h->lane_stream[l], h->ev_fork, 0);
+    if (e != cudaSuccess) return fail_cuda(h, e, "lane fork");
+  }
 
-  for (int k0 = 0; k0 < a->K; k0 += LADINE_MAX_GROUP) {
-    const int kn = (a->K - k0) < LADINE_MAX_GROUP ? (a->K - k0) : LADINE_MAX_GROUP;
+  auto group_args = [&](int k0, int kn) {
     ladine_sample_args g = *a;
     g.K = kn;
     g.xf = a->xf + (size_t)k0 * a->N * F;
@@ -452,35 +502,86 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
     g.y_out = a->y_out + k0 * kdnc;
     if (a->traj_out) g.traj_out = a->traj_out + k0 * kdnc * si.n_traj;
     if (a->prob_out) g.prob_out = a->prob_out + k0 * kdnc;
-    ChainIds ids{};
-    rc = fill_ids(h, *a, k0, kn, &ids);
-    if (rc != LADINE_OK) return rc;
+    return g;
+  };
 
-    float* d_u = reinterpret_cast<float*>(ws + o_u);
-    e = launch_guidance_u(members + k0, kn, a->N, g.y0hat, d_u, st);
-    if (e != cudaSuccess) return fail_cuda(h, e, "guidance projection kernel");
-    h->last_launches += 1;
-
-    if (!tensor) {
-      e = launch_resident(h, members + k0, g, ids, reinterpret_cast<const StepCoef*>(ws + o_coef), d_u, si.n_slots,
-                          si.n_traj, st, &h->last_launches);
-      if (e != cudaSuccess) return fail_cuda(h, e, "resident sampler launch");
-    } else {
-      TensorWorkspace tw;
-      tw.h1 = ws + o_h1;
-      tw.h2 = ws + o_h2;
-      tw.part = reinterpret_cast<float*>(ws + o_part);
-      tw.ybuf = reinterpret_cast<float*>(ws + o_y);
-      tw.u = d_u;
-      std::string err;
-      e = launch_tensor_chain(h, members + k0, g, ids, h_coef, tw, si.n_slots, si.n_traj, st, &h->last_launches, &err);
-      if (e != cudaSuccess) {
-        if (!err.empty()) return fail(h, LADINE_ERR_CUDA, err);
-        return fail_cuda(h, e, "tensor-core sampler launch");
+  int status = LADINE_OK;
+  // rounds of up to `lanes` groups; inside a round the lanes' steps are enqueued interleaved so every
+  // stream always has work queued (the launch queue is finite: enqueueing lane by lane would serialise them)
+  for (size_t g0 = 0; g0 < groups.size() && status == LADINE_OK; g0 += lanes) {
+    const int nl = (int)((groups.size() - g0) < (size_t)lanes ? (groups.size() - g0) : lanes);
+    TensorChain* chains[ladine_handle::kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+    for (int l = 0; l < nl && status == LADINE_OK; ++l) {
+      const int k0 = groups[g0 + l].first, kn = groups[g0 + l].second;
+      cudaStream_t ls = l == 0 ? st : h->lane_stream[l];
+      uint8_t* lw = ws + lane_base + lane_bytes * l;
+      const ladine_sample_args g = group_args(k0, kn);
+      ChainIds ids{};
+      status = fill_ids(h, *a, k0, kn, &ids);
+      if (status != LADINE_OK) break;
+      float* d_u = reinterpret_cast<float*>(lw + o_u);
+      e = launch_guidance_u(members + k0, kn, a->N, g.y0hat, d_u, ls);
+      if (e != cudaSuccess) { status = fail_cuda(h, e, "guidance projection kernel"); break; }
+      h->last_launches += 1;
+      if (!tensor) {
+        e = launch_resident(h, members + k0, g, ids, reinterpret_cast<const StepCoef*>(ws + o_coef), d_u, si.n_slots,
+                            si.n_traj, ls, &h->last_launches);
+        if (e != cudaSuccess) status = fail_cuda(h, e, "resident sampler launch");
+      } else {
+        TensorWorkspace tw;
+        tw.h1 = lw + o_h1;
+        tw.h2 = lw + o_h2;
+        tw.part = reinterpret_cast<float*>(lw + o_part);
+        tw.ybuf = reinterpret_cast<float*>(lw + o_y);
+        tw.u = d_u;
+        std::string err;
+        chains[l] = tensor_chain_create(h, members + k0, g, ids, h_coef, tw, si.n_slots, si.n_traj, ls,
+                                        &h->last_launches, &err, &e);
+        if (!chains[l]) status = err.empty() ? fail_cuda(h, e, "tensor-core sampler launch") : fail(h, LADINE_ERR_CUDA, err);
       }
     }
+    if (tensor) {
+      for (int t = a->t_first; t >= a->t_last && status == LADINE_OK; --t) {
+        for (int l = 0; l < nl; ++l) {
+          e = tensor_chain_step(chains[l], t, &h->last_launches);
+          if (e != cudaSuccess) { status = fail_cuda(h, e, "tensor-core sampler step launch"); break; }
+        }
+      }
+      for (int l = 0; l < nl; ++l)
+        if (chains[l]) tensor_chain_destroy(chains[l]);
+    }
   }
-  return LADINE_OK;
+  // join: the caller's stream continues only after every lane has finished (also on the error path)
+  for (int l = 1; l < lanes; ++l) {
+    cudaError_t je = cudaEventRecord(h->ev_join[l], h->lane_stream[l]);
+    if (je == cudaSuccess) je = cudaStreamWaitEvent(st, h->ev_join[l], 0);
+    if (je != cudaSuccess && status == LADINE_OK) status = fail_cuda(h, je, "lane join");
+  }
+  return status;
+}
+
+int ladine_set_option(ladine_handle* h, const char* key, int64_t value) {
+  if (!h || !key) return LADINE_ERR_INVALID;
+  if (strcmp(key, "lanes") == 0) {
+    if (value < 1 || value > ladine_handle::kMaxLanes) return fail(h, LADINE_ERR_INVALID, "lanes must be in [1, 4]");
+    h->lanes = (int)value;
+    return LADINE_OK;
+  }
+  if (strcmp(key, "pdl") == 0) {
+    set_use_pdl(value != 0);
+    return LADINE_OK;
+  }
+  if (strcmp(key, "ctas") == 0) {
+    if (value < 0 || value > 2) return fail(h, LADINE_ERR_INVALID, "ctas must be 0 (auto), 1 or 2");
+    h->ctas = (int)value;
+    return LADINE_OK;
+  }
+  if (strcmp(key, "pair_gain_permille") == 0) {
+    if (value < 500 || value > 2000) return fail(h, LADINE_ERR_INVALID, "pair_gain_permille must be in [500, 2000]");
+    h->pair_gain = value / 1000.0;
+    return LADINE_OK;
+  }
+  return fail(h, LADINE_ERR_INVALID, std::string("unknown option ") + key);
 }
 
 int ladine_fill_noise(ladine_handle* h, const ladine_sample_args* a, int32_t num_classes, float* noise) {
@@ -519,20 +620,37 @@ int ladine_set_profiling(ladine_handle* h, int enabled) {
   return LADINE_OK;
 }
 
-int ladine_get_profile(ladine_handle* h, float ms_out[3], int64_t count_out[3]) {
+int ladine_get_profile(ladine_handle* h, float ms_out[4], int64_t count_out[3]) {
   if (!h || !ms_out || !count_out) return LADINE_ERR_INVALID;
   DeviceGuard guard(h->device);
-  for (int i = 0; i < 3; ++i) {
-    ms_out[i] = 0.f;
-    count_out[i] = 0;
-  }
+  for (int i = 0; i < 4; ++i) ms_out[i] = 0.f;
+  for (int i = 0; i < 3; ++i) count_out[i] = 0;
+  std::vector<std::pair<float, float>> gemm;  // [start, end) offsets of GEMM spans from the first recorded event
+  cudaEvent_t base = h->spans.empty() ? nullptr : h->spans.front().a;
   for (auto& s : h->spans) {
     cudaError_t e = cudaEventSynchronize(s.b);
-    float ms = 0.f;
+    float ms = 0.f, t0 = 0.f;
     if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, s.a, s.b);
+    if (e == cudaSuccess && s.kind < 2) e = cudaEventElapsedTime(&t0, base, s.a);
     if (e != cudaSuccess) return fail_cuda(h, e, "profile event readback");
     ms_out[s.kind] += ms;
     count_out[s.kind] += 1;
+    if (s.kind < 2) gemm.push_back({t0, t0 + ms});
+  }
+  // union of the GEMM busy intervals (lanes overlap; a lane's span also counts time queued behind another lane)
+  std::sort(gemm.begin(), gemm.end());
+  float cur_a = 0.f, cur_b = -1.f;
+  for (auto& iv : gemm) {
+    if (cur_b < cur_a || iv.first > cur_b) {
+      if (cur_b >= cur_a) ms_out[3] += cur_b - cur_a;
+      cur_a = iv.first;
+      cur_b = iv.second;
+    } else if (iv.second > cur_b) {
+      cur_b = iv.second;
+    }
+  }
+  if (cur_b >= cur_a) ms_out[3] += cur_b - cur_a;
+  for (auto& s : h->spans) {
     h->pool.push_back(s.a);
     h->pool.push_back(s.b);
   }

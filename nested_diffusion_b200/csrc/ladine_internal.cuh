@@ -45,6 +45,14 @@ struct ladine_handle {
   // driver entry point for tensor-map encoding (resolved lazily through the runtime)
   void* encode_tiled = nullptr;
   // optional per-kernel event timing (tensor path)
+  // lanes: independent member groups run concurrently on internal streams (tensor path)
+  static constexpr int kMaxLanes = 4;
+  int lanes = 1;
+  int ctas = 0;             // 0 = choose per call, 1 = cta_group::1, 2 = cta_group::2 CTA pairs
+  double pair_gain = 1.06;   // measured throughput ratio pair/single per useful tile (see choose_ctas)
+  cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};  // [0] unused: caller's stream
+  cudaEvent_t ev_fork = nullptr;
+  cudaEvent_t ev_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
   bool profiling = false;
   struct Span { cudaEvent_t a, b; int kind; };
   std::vector<Span> spans;       // recorded since the last ladine_get_profile
@@ -72,15 +80,19 @@ struct TensorWorkspace {
   void* h1;      // [K * rows_pad, Fp] 16-bit
   void* h2;      // [K * rows_pad, Fp] 16-bit
   float* part;   // [K * rows_pad, Fp / 256, Cp]
-  float* ybuf;   // [K * rows_pad, Cp]
+  float* ybuf;   // 2 x [K * rows_pad, Cp] (ping-pong chain state)
   float* u;      // [K, N, Fp]
 };
-cudaError_t launch_tensor_chain(ladine_handle* h, const ladine_member* const* members, const ladine_sample_args& a,
-                                const ChainIds& ids, const StepCoef* h_coef, const TensorWorkspace& ws,
-                                int n_slots, int n_traj, cudaStream_t st, int64_t* launches, std::string* err);
+struct TensorChain;  // one lane: a group of members advancing through the reverse steps on one stream
+TensorChain* tensor_chain_create(ladine_handle* h, const ladine_member* const* members, const ladine_sample_args& a,
+                                 const ChainIds& ids, const StepCoef* h_coef, const TensorWorkspace& ws, int n_slots,
+                                 int n_traj, cudaStream_t st, int64_t* launches, std::string* err, cudaError_t* status);
+cudaError_t tensor_chain_step(TensorChain* c, int t, int64_t* launches);
+void tensor_chain_destroy(TensorChain* c);
 cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int layer, int t, const void* h_in, int rows,
                                void* h_out, float* part, cudaStream_t st, std::string* err);
 size_t tensor_gemm_smem_bytes(int Cp);
+void set_use_pdl(bool on);
 
 // ---- shared small kernels (ladine_api.cu) ----
 cudaError_t launch_guidance_u(const ladine_member* const* members, int K, int N, const float* y0hat, float* u,

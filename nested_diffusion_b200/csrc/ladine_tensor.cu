@@ -26,10 +26,6 @@ constexpr int BM = 128;   // rows per tile  (UMMA M)
 constexpr int BN = 256;   // cols per tile  (UMMA N)
 constexpr int BK = 64;    // K per stage    (64 x 2 B = one 128-byte swizzle row)
 constexpr int UK = 16;    // K per tcgen05.mma (kind::f16)
-constexpr int kStages = 4;
-constexpr int kABytes = BM * BK * 2;
-constexpr int kBBytes = BN * BK * 2;
-constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * BN;  // 512
 constexpr int kGemmThreads = 192;
@@ -137,90 +133,190 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 // ------------------------------------------------------------------------------------------
 struct GemmParams {
   CUtensorMap tmA;                     // activations in  [M_total, Fp] 16-bit, box 64 x 128
-  CUtensorMap tmB[LADINE_MAX_GROUP];   // member weights  [Fp, Fp]      16-bit, box 64 x 256
+  CUtensorMap tmB[LADINE_MAX_GROUP];   // member weights  [Fp, Fp]      16-bit, box 64 x (256 / CTAS)
   const float* scale[LADINE_MAX_GROUP];  // A_l[t] row of each member (already offset to row t), x log2e
   const float* shift[LADINE_MAX_GROUP];  // C_l[t] row, x log2e
   const float* W4[LADINE_MAX_GROUP];     // [Cp, Fp]  (layer 3 only)
   void* h_out;                         // layer 2: [M_total, Fp] 16-bit
   float* part;                         // layer 3: [M_total, NB, Cp]
   int Fp, NB, KB;                      // padded feature dim, N tiles (Fp/256), K blocks (Fp/64)
-  int mblk;                            // row tiles per member
+  int mblk;                            // row tiles (128 * CTAS rows each) per member
   int rows;                            // valid rows per member
-  int rows_pad;                        // mblk * 128
+  int rows_pad;                        // mblk * 128 * CTAS
   int num_tiles;                       // K * mblk * NB
   uint32_t idesc;
 };
 
+// pipeline geometry per CTA: CTAS = 1 -> A 128x64 + B 256x64 per stage; CTAS = 2 (cta_group::2, the
+// CTA pair computes a 256x256 tile) -> A 128x64 + the CTA's half of B 128x64 per stage, so deeper ring
+template <int CTAS>
+struct GemmCfg {
+  static constexpr int kStages = CTAS == 1 ? 4 : 6;
+  static constexpr int kBRows = BN / CTAS;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = kBRows * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+};
+constexpr int kMaxStages = 6;
+
 struct __align__(8) GemmBarriers {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
   uint64_t acc_full[kAccStages];
   uint64_t acc_empty[kAccStages];
   uint32_t tmem_base;
   uint32_t pad;
 };
 
+// 256-bit global store (one full 32-byte sector per thread)
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 
-template <int LAYER, typename T16, int CP>
+// ---- programmatic dependent launch (PDL) ----
+// Every kernel of the chain is launched with programmaticStreamSerialization: its CTAs may start while the
+// previous kernel drains, run their prologue (barrier init, TMEM alloc, descriptor prefetch), and must
+// execute pdl_wait() before touching any global memory the previous kernel wrote (or that it still reads).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---- cluster / cta_group::2 helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (as CUTLASS ClusterBarrier::arrive): an explicit .release.cluster lowers to a GPU-scope
+  // MEMBAR + ERRBAR, which cost ~1 us per arrive when it sat in the per-stage producer loop
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of one CTA of a pair; completion bytes are signalled on `bar` (a shared::cluster address, normally
+// the leader CTA's barrier)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of the pair's MMAs, delivered to the barrier at the same offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+
+template <int LAYER, typename T16, int CP, int CTAS>
 __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<CTAS>;
+  constexpr int kStages = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                               // kStages x 16 KiB
-  uint8_t* sB = smem + kStages * kABytes;           // kStages x 32 KiB
-  float* sEpi = reinterpret_cast<float*>(smem + kStages * kStageBytes);  // scale[256] shift[256] (W4[CP][256])
+  uint8_t* sA = smem;                                    // kStages x 16 KiB
+  uint8_t* sB = smem + kStages * Cfg::kABytes;           // kStages x 32 (16) KiB
+  float* sEpi = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);  // scale[256] shift[256] (W4[CP][256])
   GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(sEpi + (LAYER == 3 ? BN * (2 + CP) : 2 * BN));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;   // position in the CTA pair; 0 issues the MMAs
+  const int unit = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // tile-scheduling unit (CTA or pair)
+  const int n_units = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
+      // one arrival: the (leader's) producer arrive.expect_tx; in a pair the peer's TMA bytes complete on the
+      // leader's barrier too (its loads for round r+1 cannot start before phase r completed: they wait on
+      // the multicast `empty` commit of the MMAs that consumed round r)
       mbar_init(smem_u32(&bars->full[s]), 1);
       mbar_init(smem_u32(&bars->empty[s]), 1);
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(smem_u32(&bars->acc_full[s]), 1);
-      mbar_init(smem_u32(&bars->acc_empty[s]), kEpiThreads / 32);
+      mbar_init(smem_u32(&bars->acc_empty[s]), CTAS * (kEpiThreads / 32));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&p.tmA);
   }
-  if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
+  if (warp == 2) {
+    if (CTAS == 2) tmem_alloc_pair(smem_u32(&bars->tmem_base), kTmemCols);
+    else tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_launch_dependents();  // the next kernel's CTAs can take this SM the moment this CTA retires
+  pdl_wait();               // everything below reads/writes buffers shared with the previous kernels
 
   const int tiles_per_member = p.mblk * p.NB;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (one per CTA) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < p.num_tiles; tile += n_units) {
         const int member = tile / tiles_per_member;
         const int rem = tile - member * tiles_per_member;
         const int nb = rem / p.mblk, mb = rem - nb * p.mblk;
-        const int arow = member * p.rows_pad + mb * BM;
+        const int arow = member * p.rows_pad + mb * (BM * CTAS) + (int)rank * BM;
+        const int brow = nb * BN + (int)rank * Cfg::kBRows;
         const CUtensorMap* tb = &p.tmB[member];
         for (int kb = 0; kb < p.KB; ++kb) {
           mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u, 0);
           const uint32_t fb = smem_u32(&bars->full[stage]);
-          mbar_arrive_expect_tx(fb, kStageBytes);
-          tma_load_2d(smem_u32(sA + stage * kABytes), &p.tmA, fb, kb * BK, arow);
-          tma_load_2d(smem_u32(sB + stage * kBBytes), tb, fb, kb * BK, nb * BN);
+          if (CTAS == 1) {
+            mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+            tma_load_2d(smem_u32(sA + stage * Cfg::kABytes), &p.tmA, fb, kb * BK, arow);
+            tma_load_2d(smem_u32(sB + stage * Cfg::kBBytes), tb, fb, kb * BK, brow);
+          } else {
+            const uint32_t lfb = mapa_rank(fb, 0);  // both CTAs' bytes complete on the leader's barrier
+            if (rank == 0) mbar_arrive_expect_tx(fb, 2 * Cfg::kStageBytes);
+            tma_load_2d_pair(smem_u32(sA + stage * Cfg::kABytes), &p.tmA, lfb, kb * BK, arow);
+            tma_load_2d_pair(smem_u32(sB + stage * Cfg::kBBytes), tb, lfb, kb * BK, brow);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (single thread; leader CTA of a pair) =====================
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < p.num_tiles; tile += n_units, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(smem_u32(&bars->acc_empty[as]), aphase ^ 1u, 1);
@@ -229,21 +325,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
         for (int kb = 0; kb < p.KB; ++kb) {
           mbar_wait(smem_u32(&bars->full[stage]), phase, 2);
           tc_fence_after();
-          const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * kABytes));
-          const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * kBBytes));
+          const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * Cfg::kABytes));
+          const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * Cfg::kBBytes));
 #pragma unroll
           for (int k4 = 0; k4 < BK / UK; ++k4) {
             // +32 bytes per K=16 slice inside the 128-byte swizzle row: +2 in the >>4 address field
-            umma_f16(d_tmem, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), p.idesc, (uint32_t)((kb | k4) != 0));
+            if (CTAS == 2)
+              umma_f16_pair(d_tmem, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), p.idesc, (uint32_t)((kb | k4) != 0));
+            else
+              umma_f16(d_tmem, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), p.idesc, (uint32_t)((kb | k4) != 0));
           }
-          umma_commit(smem_u32(&bars->empty[stage]));  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if (CTAS == 2) umma_commit_pair(smem_u32(&bars->empty[stage]));
+          else umma_commit(smem_u32(&bars->empty[stage]));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(smem_u32(&bars->acc_full[as]));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (CTAS == 2) umma_commit_pair(smem_u32(&bars->acc_full[as]));
+        else umma_commit(smem_u32(&bars->acc_full[as]));
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..5), this CTA's 128 rows x 256 columns =====================
     const int et = threadIdx.x - 64;         // 0..127
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
     const int row_in_tile = quad * 32 + lane;
@@ -251,7 +354,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
     float* sShift = sEpi + BN;
     float* sW4 = sEpi + 2 * BN;              // [CP][BN]
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < p.num_tiles; tile += n_units, ++it) {
       const int member = tile / tiles_per_member;
       const int rem = tile - member * tiles_per_member;
       const int nb = rem / p.mblk, mb = rem - nb * p.mblk;
@@ -286,7 +389,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
       mbar_wait(smem_u32(&bars->acc_full[as]), aphase, 3);
       tc_fence_after();
 
-      const int row_m = mb * BM + row_in_tile;          // row within the member
+      const int row_m = mb * (BM * CTAS) + (int)rank * BM + row_in_tile;   // row within the member
       const bool valid = row_m < p.rows;
       const size_t grow = (size_t)member * p.rows_pad + row_m;
       const uint32_t taddr = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quad * 32) << 16);
@@ -311,15 +414,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
         }
         if (LAYER == 2) {
           if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<T16*>(p.h_out) + grow * p.Fp + nb * BN + ch * 32);
+            // 32 consecutive 16-bit outputs of this row = 64 B = two full 32-byte sectors: 256-bit stores
+            T16* dst = reinterpret_cast<T16*>(p.h_out) + grow * p.Fp + nb * BN + ch * 32;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              o.x = Pack16<T16>::pack(hcol[8 * q + 0], hcol[8 * q + 1]);
-              o.y = Pack16<T16>::pack(hcol[8 * q + 2], hcol[8 * q + 3]);
-              o.z = Pack16<T16>::pack(hcol[8 * q + 4], hcol[8 * q + 5]);
-              o.w = Pack16<T16>::pack(hcol[8 * q + 6], hcol[8 * q + 7]);
-              dst[q] = o;
+            for (int q = 0; q < 2; ++q) {
+              uint32_t o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = Pack16<T16>::pack(hcol[16 * q + 2 * i], hcol[16 * q + 2 * i + 1]);
+              st_global_256(dst + 16 * q, o);
             }
           }
         } else {
@@ -338,10 +440,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
           }
         }
       }
-      // accumulator stage drained: hand it back to the MMA warp
+      // accumulator stage drained: hand it back to the MMA issuer (in the leader CTA)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[as]));
+      if (lane == 0) {
+        const uint32_t eb = smem_u32(&bars->acc_empty[as]);
+        if (CTAS == 2) mbar_arrive_cluster(mapa_rank(eb, 0));
+        else mbar_arrive(eb);
+      }
       if (LAYER == 3 && valid) {
         float* dst = p.part + (grow * p.NB + nb) * CP;
 #pragma unroll
@@ -351,10 +457,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();   // pair: the peer's smem/TMEM stay live until both are done
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -369,7 +476,8 @@ struct TailHeadParams {
   const float* W1y[LADINE_MAX_GROUP];  // [Fp, Cp]
   const float* b4[LADINE_MAX_GROUP];
   const float* part;   // [M_total, NB, Cp]
-  float* ybuf;         // [M_total, Cp]  chain state
+  const float* y_prev; // [M_total, Cp]  chain state before this step (ping-pong: column-split CTAs all read it)
+  float* y_next;       // [M_total, Cp]  chain state after this step (written by column split 0)
   const float* xf;     // [K, N, Fin]
   const float* u;      // [K, N, Fp]
   const float* ytmean; // [K, N, C]
@@ -386,20 +494,26 @@ struct TailHeadParams {
   int t;               // table index of the step being finished (kInit: unused)
   int slot;            // noise slot / trajectory entry consumed-written by this launch
   int traj_entry;
-  int N, D, C, Fin, Fp, NB, rows_pad, n_slots, n_traj, dchunk, write_out;
+  int N, D, C, Fin, Fp, NB, rows_pad, n_slots, n_traj, dchunk, write_out, colsplit;
 };
 
-constexpr int kTailThreads = 256;
+constexpr int kTailThreads = 128;
+constexpr int kTailCols = kTailThreads * 8;  // features per CTA: 8 per thread
 constexpr int kTailMaxRows = 32;  // draws handled per CTA
 
 template <int MODE, typename T16, int CP>
 __global__ void __launch_bounds__(kTailThreads) tailhead_kernel(const __grid_constant__ TailHeadParams p) {
   __shared__ float sY[kTailMaxRows * CP];
-  const int n = blockIdx.x, k = blockIdx.y;
+  // grid.x = N * colsplit: CTA (n, cs) produces features [cs * kTailCols, (cs+1) * kTailCols) of image n's draws.
+  // Every column split recomputes the (tiny) tail; split 0 alone publishes y / outputs.
+  const int n = blockIdx.x / p.colsplit, cs = blockIdx.x - n * p.colsplit, k = blockIdx.y;
+  const bool publish = cs == 0;
   const int d0 = blockIdx.z * p.dchunk;
   const int nd = min(p.dchunk, p.D - d0);
   const int tid = threadIdx.x;
   const int C = p.C;
+  pdl_launch_dependents();
+  pdl_wait();
 
   // ---------------- tail: finish step t for rows (k, n, d0..d0+nd) ----------------
   for (int i = tid; i < nd * C; i += kTailThreads) {
@@ -420,7 +534,7 @@ __global__ void __launch_bounds__(kTailThreads) tailhead_kernel(const __grid_con
       float eps = __ldg(p.b4[k] + c);
       const float* pp = p.part + (grow * p.NB) * CP + c;
       for (int nb = 0; nb < p.NB; ++nb) eps += pp[nb * CP];  // fixed order: deterministic
-      const float y = p.ybuf[grow * CP + c];
+      const float y = p.y_prev[grow * CP + c];
       if (p.t > 0) {
         const float z = p.noise ? __ldg(p.noise + ((((size_t)k * p.D + d) * p.n_slots + p.slot) * p.N + n) * C + c)
                                 : philox_normal(p.seed, p.ids.chain(k, d, n), (uint32_t)p.slot, c);
@@ -429,15 +543,17 @@ __global__ void __launch_bounds__(kTailThreads) tailhead_kernel(const __grid_con
         yn = y0_reparam_op(p.coef, y, mu, eps);
       }
     }
-    p.ybuf[grow * CP + c] = yn;
     sY[dl * CP + c] = yn;
-    if (p.traj_out && p.traj_entry >= 0)
-      p.traj_out[((((size_t)k * p.D + d) * p.n_traj + p.traj_entry) * p.N + n) * C + c] = yn;
-    if (p.write_out) p.y_out[(((size_t)k * p.D + d) * p.N + n) * C + c] = yn;
+    if (publish) {
+      p.y_next[grow * CP + c] = yn;
+      if (p.traj_out && p.traj_entry >= 0)
+        p.traj_out[((((size_t)k * p.D + d) * p.n_traj + p.traj_entry) * p.N + n) * C + c] = yn;
+      if (p.write_out) p.y_out[(((size_t)k * p.D + d) * p.N + n) * C + c] = yn;
+    }
   }
-  if (MODE == kFinal && !p.write_out) return;
+  if (MODE == kFinal && !(p.write_out && p.prob_out)) return;
   __syncthreads();
-  if (p.write_out && p.prob_out) {
+  if (publish && p.write_out && p.prob_out) {
     // softmax(-(y-1)^2 / temperature) -- classification_train_separately.py:392-398
     for (int dl = tid; dl < nd; dl += kTailThreads) {
       float mx = -INFINITY;
@@ -463,7 +579,7 @@ __global__ void __launch_bounds__(kTailThreads) tailhead_kernel(const __grid_con
   // thread owns 8 consecutive features; their per-column constants stay in registers across draws
   const float* xfrow = p.xf + ((size_t)k * p.N + n) * p.Fin;
   const float* urow = p.u + ((size_t)k * p.N + n) * p.Fp;
-  for (int f0 = tid * 8; f0 < p.Fp; f0 += kTailThreads * 8) {
+  for (int f0 = cs * kTailCols + tid * 8; f0 < p.Fp; f0 += p.colsplit * kTailCols) {
     float a1[8], c1[8], uu[8], xx[8], w1[8][CP];
     {
       const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.A1[k] + f0));
@@ -548,29 +664,56 @@ bool make_tmap(ladine_handle* h, CUtensorMap* out, const void* base, uint64_t ro
 
 // instruction descriptor for kind::f16 (PTX ISA "Instruction descriptor"): D format F32 (1) at [4,6);
 // A/B format (0 = F16, 1 = BF16) at [7,10)/[10,13); A,B K-major (0) at 15/16; N>>3 at [17,23); M>>4 at [24,29)
-uint32_t make_idesc(bool bf16) {
+uint32_t make_idesc(bool bf16, int ctas) {
   const uint32_t fmt = bf16 ? 1u : 0u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * ctas) >> 4) << 24);
 }
 
-template <int LAYER, typename T16, int CP>
+bool g_use_pdl = true;  // process-wide; toggled through ladine_set_option("pdl")
+
+template <int LAYER, typename T16, int CP, int CTAS>
 cudaError_t launch_gemm_t(const GemmParams& p, int grid, cudaStream_t st) {
   const size_t smem = tensor_gemm_smem_bytes(CP);
-  auto kern = trunk_gemm_kernel<LAYER, T16, CP>;
+  auto kern = trunk_gemm_kernel<LAYER, T16, CP, CTAS>;
   // cheap (host-side table update); done per launch so it is right for every device of the process
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kGemmThreads, smem, st>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[na].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  ++na;
+  if (CTAS == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
-template <int LAYER>
-cudaError_t launch_gemm(const GemmParams& p, int grid, bool bf16, int Cp, cudaStream_t st) {
-#define LADINE_GEMM_CASE(CPV)                                                              \
-  case CPV:                                                                                \
-    return bf16 ? launch_gemm_t<LAYER, __nv_bfloat16, CPV>(p, grid, st)                    \
-                : launch_gemm_t<LAYER, __half, CPV>(p, grid, st);
-  if (LAYER == 2) Cp = 2;  // the layer-2 epilogue does not depend on the class count
+// grid size for a GEMM launch: one CTA (or CTA pair) per tile-scheduling unit, at most one per SM
+int gemm_grid(const ladine_handle* h, int num_tiles, int ctas) {
+  const int units = h->sm_count / ctas;
+  return (num_tiles < units ? num_tiles : units) * ctas;
+}
+
+template <int LAYER, typename T16>
+cudaError_t launch_gemm_c(const GemmParams& p, int grid, int Cp, int ctas, cudaStream_t st) {
+  if (LAYER == 2) {  // the layer-2 epilogue does not depend on the class count
+    return ctas == 2 ? launch_gemm_t<2, T16, 2, 2>(p, grid, st) : launch_gemm_t<2, T16, 2, 1>(p, grid, st);
+  }
+#define LADINE_GEMM_CASE(CPV)                                                                          \
+  case CPV:                                                                                            \
+    return ctas == 2 ? launch_gemm_t<3, T16, CPV, 2>(p, grid, st) : launch_gemm_t<3, T16, CPV, 1>(p, grid, st);
   switch (Cp) {
     LADINE_GEMM_CASE(2)
     LADINE_GEMM_CASE(4)
@@ -581,22 +724,44 @@ cudaError_t launch_gemm(const GemmParams& p, int grid, bool bf16, int Cp, cudaSt
   return cudaErrorInvalidValue;
 }
 
+template <int LAYER>
+cudaError_t launch_gemm(const GemmParams& p, int grid, bool bf16, int Cp, int ctas, cudaStream_t st) {
+  return bf16 ? launch_gemm_c<LAYER, __nv_bfloat16>(p, grid, Cp, ctas, st)
+              : launch_gemm_c<LAYER, __half>(p, grid, Cp, ctas, st);
+}
+
+template <int MODE, typename T16, int CP>
+cudaError_t launch_tail_t(const TailHeadParams& p, dim3 grid, cudaStream_t st) {
+  auto kern = tailhead_kernel<MODE, T16, CP>;
+  // same shared-memory carveout as the GEMM kernels, so the SMs are not reconfigured at every kernel boundary
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kTailThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
 template <int MODE>
 cudaError_t launch_tail(const TailHeadParams& p, dim3 grid, bool bf16, int Cp, cudaStream_t st) {
 #define LADINE_TAIL_CASE(CPV)                                                              \
   case CPV:                                                                                \
-    if (bf16) tailhead_kernel<MODE, __nv_bfloat16, CPV><<<grid, kTailThreads, 0, st>>>(p); \
-    else tailhead_kernel<MODE, __half, CPV><<<grid, kTailThreads, 0, st>>>(p);             \
-    break;
+    return bf16 ? launch_tail_t<MODE, __nv_bfloat16, CPV>(p, grid, st) : launch_tail_t<MODE, __half, CPV>(p, grid, st);
   switch (Cp) {
     LADINE_TAIL_CASE(2)
     LADINE_TAIL_CASE(4)
     LADINE_TAIL_CASE(8)
     LADINE_TAIL_CASE(16)
-    default: return cudaErrorInvalidValue;
   }
 #undef LADINE_TAIL_CASE
-  return cudaGetLastError();
+  return cudaErrorInvalidValue;
 }
 
 struct ProfSpan {
@@ -630,108 +795,154 @@ struct ProfSpan {
 }  // namespace
 
 size_t tensor_gemm_smem_bytes(int Cp) {
-  return 1024 /*alignment slack*/ + (size_t)kStages * kStageBytes + sizeof(float) * BN * (2 + Cp) + sizeof(GemmBarriers);
+  static_assert(GemmCfg<1>::kStages * GemmCfg<1>::kStageBytes == GemmCfg<2>::kStages * GemmCfg<2>::kStageBytes,
+                "both pipeline geometries use the same ring size");
+  return 1024 /*alignment slack*/ + (size_t)GemmCfg<1>::kStages * GemmCfg<1>::kStageBytes +
+         sizeof(float) * BN * (2 + Cp) + sizeof(GemmBarriers);
 }
 
-cudaError_t launch_tensor_chain(ladine_handle* h, const ladine_member* const* members, const ladine_sample_args& a,
-                                const ChainIds& ids, const StepCoef* h_coef, const TensorWorkspace& ws, int n_slots,
-                                int n_traj, cudaStream_t st, int64_t* launches, std::string* err) {
-  const ladine_member* m0 = members[0];
-  const bool bf16 = m0->precision == LADINE_PREC_BF16;
-  const int Fp = m0->Fp, Cp = m0->Cp, K = a.K;
-  const int rows = a.N * a.D;
-  const int mblk = (rows + BM - 1) / BM;
-  const int rows_pad = mblk * BM;
-  const size_t m_total = (size_t)K * rows_pad;
+// 1 = cta_group::1 tiles of 128 rows, 2 = CTA pairs (cta_group::2) on 256-row tiles.  Pairs halve the
+// B-operand shared-memory/L2 traffic per SM but pad each member's rows to a multiple of 256.
+void set_use_pdl(bool on) { g_use_pdl = on; }
 
-  cudaError_t e = resolve_encode(h, err);
-  if (e != cudaSuccess) return e;
+int choose_ctas(const ladine_handle* h, int rows) {
+  if (h->ctas == 1 || h->ctas == 2) return h->ctas;
+  const double eff1 = (double)rows / (((rows + 127) / 128) * 128);
+  const double eff2 = (double)rows / (((rows + 255) / 256) * 256);
+  return eff2 * h->pair_gain > eff1 ? 2 : 1;
+}
 
+// One lane = one group of members advancing through the reverse steps on its own stream.  Lanes are
+// independent chains, so running them on separate streams lets the hardware hand SMs from one lane's
+// GEMM CTAs to the next lane's as they retire (no inter-kernel drain/launch gap) and hides the
+// tail/head kernel of one lane under the GEMMs of the other.
+struct TensorChain {
+  ladine_handle* h;
+  const ladine_member* const* members;
+  ladine_sample_args a;
+  const StepCoef* h_coef;
+  cudaStream_t st;
   GemmParams g2{}, g3{};
-  if (!make_tmap(h, &g2.tmA, ws.h1, m_total, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
-  if (!make_tmap(h, &g3.tmA, ws.h2, m_total, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
-  for (int k = 0; k < K; ++k) {
-    if (!make_tmap(h, &g2.tmB[k], members[k]->W2h, Fp, Fp, BN, bf16, err)) return cudaErrorInvalidValue;
-    if (!make_tmap(h, &g3.tmB[k], members[k]->W3h, Fp, Fp, BN, bf16, err)) return cudaErrorInvalidValue;
-    g3.W4[k] = members[k]->W4;
-  }
-  for (GemmParams* g : {&g2, &g3}) {
-    g->Fp = Fp;
-    g->NB = Fp / BN;
-    g->KB = Fp / BK;
-    g->mblk = mblk;
-    g->rows = rows;
-    g->rows_pad = rows_pad;
-    g->num_tiles = K * mblk * (Fp / BN);
-    g->idesc = make_idesc(bf16);
-  }
-  g2.h_out = ws.h2;
-  g3.part = ws.part;
-  const int grid = g2.num_tiles < h->sm_count ? g2.num_tiles : h->sm_count;
-
   TailHeadParams tp{};
-  for (int k = 0; k < K; ++k) {
-    tp.W1y[k] = members[k]->W1y;
-    tp.b4[k] = members[k]->b4;
-  }
-  tp.part = ws.part;
-  tp.ybuf = ws.ybuf;
-  tp.xf = a.xf;
-  tp.u = ws.u;
-  tp.ytmean = a.ytmean;
-  tp.y_init = a.y_init;
-  tp.noise = a.noise;
-  tp.h1 = ws.h1;
-  tp.y_out = a.y_out;
-  tp.traj_out = a.traj_out;
-  tp.prob_out = a.prob_out;
-  tp.temperature = a.prob_out ? a.temperature : 1.0f;
-  tp.seed = a.seed;
-  tp.ids = ids;
-  tp.N = a.N;
-  tp.D = a.D;
-  tp.C = m0->C;
-  tp.Fin = m0->F;
-  tp.Fp = Fp;
-  tp.NB = Fp / BN;
-  tp.rows_pad = rows_pad;
-  tp.n_slots = n_slots;
-  tp.n_traj = n_traj;
-  tp.dchunk = a.D < kTailMaxRows ? a.D : kTailMaxRows;
-  const dim3 tgrid(a.N, K, (a.D + tp.dchunk - 1) / tp.dchunk);
-  const int slot_base = a.y_init ? 0 : 1;
+  dim3 tgrid;
+  int grid = 0, K = 0, Fp = 0, Cp = 0, slot_base = 0, ctas = 1, ycur = 0;
+  float* ybuf[2] = {nullptr, nullptr};
+  bool bf16 = false;
 
-  auto set_head_rows = [&](int t_next) {
+  void set_head_rows(int t_next) {
     for (int k = 0; k < K; ++k) {
       tp.A1[k] = members[k]->A[0] + (size_t)t_next * Fp;
       tp.C1[k] = members[k]->Cc[0] + (size_t)t_next * Fp;
     }
-  };
+  }
 
-  // y_T (or the caller's y) and h1 for the first step
-  set_head_rows(a.t_first);
-  tp.slot = 0;
-  tp.traj_entry = a.y_init ? -1 : 0;
-  tp.write_out = 0;
-  e = launch_tail<kInit>(tp, tgrid, bf16, Cp, st);
-  if (e != cudaSuccess) return e;
-  ++*launches;
+  cudaError_t init(ladine_handle* h_, const ladine_member* const* members_, const ladine_sample_args& a_,
+                   const ChainIds& ids, const StepCoef* h_coef_, const TensorWorkspace& ws, int n_slots, int n_traj,
+                   cudaStream_t st_, int64_t* launches, std::string* err) {
+    h = h_;
+    members = members_;
+    a = a_;
+    h_coef = h_coef_;
+    st = st_;
+    const ladine_member* m0 = members[0];
+    bf16 = m0->precision == LADINE_PREC_BF16;
+    Fp = m0->Fp;
+    Cp = m0->Cp;
+    K = a.K;
+    const int rows = a.N * a.D;
+    ctas = choose_ctas(h, rows);
+    const int tile_rows = BM * ctas;
+    const int mblk = (rows + tile_rows - 1) / tile_rows;
+    const int rows_pad = mblk * tile_rows;
+    const size_t m_total = (size_t)K * rows_pad;
 
-  for (int t = a.t_first; t >= a.t_last; --t) {
+    cudaError_t e = resolve_encode(h, err);
+    if (e != cudaSuccess) return e;
+    if (!make_tmap(h, &g2.tmA, ws.h1, m_total, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
+    if (!make_tmap(h, &g3.tmA, ws.h2, m_total, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
+    for (int k = 0; k < K; ++k) {
+      if (!make_tmap(h, &g2.tmB[k], members[k]->W2h, Fp, Fp, BN / ctas, bf16, err)) return cudaErrorInvalidValue;
+      if (!make_tmap(h, &g3.tmB[k], members[k]->W3h, Fp, Fp, BN / ctas, bf16, err)) return cudaErrorInvalidValue;
+      g3.W4[k] = members[k]->W4;
+    }
+    for (GemmParams* g : {&g2, &g3}) {
+      g->Fp = Fp;
+      g->NB = Fp / BN;
+      g->KB = Fp / BK;
+      g->mblk = mblk;
+      g->rows = rows;
+      g->rows_pad = rows_pad;
+      g->num_tiles = K * mblk * (Fp / BN);
+      g->idesc = make_idesc(bf16, ctas);
+    }
+    g2.h_out = ws.h2;
+    g3.part = ws.part;
+    grid = gemm_grid(h, g2.num_tiles, ctas);
+
+    for (int k = 0; k < K; ++k) {
+      tp.W1y[k] = members[k]->W1y;
+      tp.b4[k] = members[k]->b4;
+    }
+    tp.part = ws.part;
+    ybuf[0] = ws.ybuf;
+    ybuf[1] = ws.ybuf + m_total * Cp;
+    ycur = 0;
+    tp.xf = a.xf;
+    tp.u = ws.u;
+    tp.ytmean = a.ytmean;
+    tp.y_init = a.y_init;
+    tp.noise = a.noise;
+    tp.h1 = ws.h1;
+    tp.y_out = a.y_out;
+    tp.traj_out = a.traj_out;
+    tp.prob_out = a.prob_out;
+    tp.temperature = a.prob_out ? a.temperature : 1.0f;
+    tp.seed = a.seed;
+    tp.ids = ids;
+    tp.N = a.N;
+    tp.D = a.D;
+    tp.C = m0->C;
+    tp.Fin = m0->F;
+    tp.Fp = Fp;
+    tp.NB = Fp / BN;
+    tp.rows_pad = rows_pad;
+    tp.n_slots = n_slots;
+    tp.n_traj = n_traj;
+    tp.dchunk = a.D < kTailMaxRows ? a.D : kTailMaxRows;
+    tp.colsplit = (Fp + kTailCols - 1) / kTailCols;
+    tgrid = dim3(a.N * tp.colsplit, K, (a.D + tp.dchunk - 1) / tp.dchunk);
+    slot_base = a.y_init ? 0 : 1;
+
+    // y_T (or the caller's y) and h1 for the first step
+    set_head_rows(a.t_first);
+    tp.slot = 0;
+    tp.traj_entry = a.y_init ? -1 : 0;
+    tp.write_out = 0;
+    tp.y_prev = ybuf[ycur];
+    tp.y_next = ybuf[ycur ^ 1];
+    ycur ^= 1;
+    e = launch_tail<kInit>(tp, tgrid, bf16, Cp, st);
+    if (e == cudaSuccess) ++*launches;
+    return e;
+  }
+
+  // enqueue reverse step t: GEMM layer 2, GEMM layer 3, tail (+ head of step t-1)
+  cudaError_t step(int t, int64_t* launches) {
     for (int k = 0; k < K; ++k) {
       g2.scale[k] = members[k]->A[1] + (size_t)t * Fp;
       g2.shift[k] = members[k]->Cc[1] + (size_t)t * Fp;
       g3.scale[k] = members[k]->A[2] + (size_t)t * Fp;
       g3.shift[k] = members[k]->Cc[2] + (size_t)t * Fp;
     }
+    cudaError_t e;
     {
       ProfSpan ps(h, st, 0);
-      e = launch_gemm<2>(g2, grid, bf16, Cp, st);
+      e = launch_gemm<2>(g2, grid, bf16, Cp, ctas, st);
     }
     if (e != cudaSuccess) return e;
     {
       ProfSpan ps(h, st, 1);
-      e = launch_gemm<3>(g3, grid, bf16, Cp, st);
+      e = launch_gemm<3>(g3, grid, bf16, Cp, ctas, st);
     }
     if (e != cudaSuccess) return e;
     tp.coef = h_coef[t];
@@ -740,6 +951,9 @@ cudaError_t launch_tensor_chain(ladine_handle* h, const ladine_member* const* me
     tp.traj_entry = slot_base + (a.t_first - t);
     const bool last = (t == a.t_last);
     tp.write_out = last ? 1 : 0;
+    tp.y_prev = ybuf[ycur];
+    tp.y_next = ybuf[ycur ^ 1];
+    ycur ^= 1;
     {
       ProfSpan ps(h, st, 2);
       if (last) {
@@ -749,11 +963,24 @@ cudaError_t launch_tensor_chain(ladine_handle* h, const ladine_member* const* me
         e = launch_tail<kMid>(tp, tgrid, bf16, Cp, st);
       }
     }
-    if (e != cudaSuccess) return e;
-    *launches += 3;
+    if (e == cudaSuccess) *launches += 3;
+    return e;
   }
-  return cudaSuccess;
+};
+
+TensorChain* tensor_chain_create(ladine_handle* h, const ladine_member* const* members, const ladine_sample_args& a,
+                                 const ChainIds& ids, const StepCoef* h_coef, const TensorWorkspace& ws, int n_slots,
+                                 int n_traj, cudaStream_t st, int64_t* launches, std::string* err, cudaError_t* status) {
+  TensorChain* c = new TensorChain();
+  *status = c->init(h, members, a, ids, h_coef, ws, n_slots, n_traj, st, launches, err);
+  if (*status != cudaSuccess) {
+    delete c;
+    return nullptr;
+  }
+  return c;
 }
+cudaError_t tensor_chain_step(TensorChain* c, int t, int64_t* launches) { return c->step(t, launches); }
+void tensor_chain_destroy(TensorChain* c) { delete c; }
 
 cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int layer, int t, const void* h_in, int rows,
                                void* h_out, float* part, cudaStream_t st, std::string* err) {
@@ -761,10 +988,12 @@ cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int lay
   cudaError_t e = resolve_encode(h, err);
   if (e != cudaSuccess) return e;
   const int Fp = m->Fp;
-  const int mblk = (rows + BM - 1) / BM;
+  const int ctas = (h->ctas == 2) ? 2 : 1;  // debug entry: caller-provided buffers are padded to 128 rows unless "ctas"=2
+  const int tile_rows = BM * ctas;
+  const int mblk = (rows + tile_rows - 1) / tile_rows;
   GemmParams g{};
-  if (!make_tmap(h, &g.tmA, h_in, (uint64_t)mblk * BM, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
-  if (!make_tmap(h, &g.tmB[0], layer == 2 ? m->W2h : m->W3h, Fp, Fp, BN, bf16, err)) return cudaErrorInvalidValue;
+  if (!make_tmap(h, &g.tmA, h_in, (uint64_t)mblk * tile_rows, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
+  if (!make_tmap(h, &g.tmB[0], layer == 2 ? m->W2h : m->W3h, Fp, Fp, BN / ctas, bf16, err)) return cudaErrorInvalidValue;
   g.scale[0] = m->A[layer - 1] + (size_t)t * Fp;
   g.shift[0] = m->Cc[layer - 1] + (size_t)t * Fp;
   g.W4[0] = m->W4;
@@ -775,11 +1004,11 @@ cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int lay
   g.KB = Fp / BK;
   g.mblk = mblk;
   g.rows = rows;
-  g.rows_pad = mblk * BM;
+  g.rows_pad = mblk * tile_rows;
   g.num_tiles = mblk * g.NB;
-  g.idesc = make_idesc(bf16);
-  const int grid = g.num_tiles < h->sm_count ? g.num_tiles : h->sm_count;
-  return layer == 2 ? launch_gemm<2>(g, grid, bf16, m->Cp, st) : launch_gemm<3>(g, grid, bf16, m->Cp, st);
+  g.idesc = make_idesc(bf16, ctas);
+  const int grid = gemm_grid(h, g.num_tiles, ctas);
+  return layer == 2 ? launch_gemm<2>(g, grid, bf16, m->Cp, ctas, st) : launch_gemm<3>(g, grid, bf16, m->Cp, ctas, st);
 }
 
 }  // namespace ladine

@@ -271,8 +271,16 @@ def set_profiling(device_index: int, enabled: bool) -> None:
 
 def get_profile(device_index: int) -> dict:
     """{'gemm2': (ms, launches), 'gemm3': (...), 'tailhead': (...)} since the last call (synchronises)."""
-    ms = (C.c_float * 3)()
+    ms = (C.c_float * 4)()
     cnt = (C.c_int64 * 3)()
     h = _capi.handle(device_index)
     _capi.check(h, _capi.load().ladine_get_profile(h, ms, cnt))
-    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("gemm2", "gemm3", "tailhead"))}
+    out = {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("gemm2", "gemm3", "tailhead"))}
+    out["gemm_busy_ms"] = float(ms[3])  # union of GEMM spans (lanes overlap)
+    return out
+
+
+def set_option(device_index: int, key: str, value: int) -> None:
+    """ladine_set_option: e.g. ``set_option(0, "lanes", 2)``."""
+    h = _capi.handle(device_index)
+    _capi.check(h, _capi.load().ladine_set_option(h, key.encode(), int(value)))

@@ -68,7 +68,9 @@ class EnsembleResult:
 class NestedEnsemble:
     """K packed members kept resident on one GPU (no per-batch CPU<->GPU shuttle)."""
 
-    def __init__(self, models: Sequence, precision: str = "auto", member_ids: Optional[Sequence[int]] = None):
+    def __init__(self, models: Sequence, precision: str = "auto", member_ids: Optional[Sequence[int]] = None,
+                 max_rows_per_call: int = 262144):
+        self.max_rows_per_call = int(max_rows_per_call)  # chains (images x draws) per member per launch group
         if len(models) < 1:
             raise ValueError("need at least one member")
         self.models = list(models)
@@ -97,11 +99,24 @@ class NestedEnsemble:
         if noise is None and seed is None:
             seed = engine.fresh_seed()
         coef = coef_table(alphas, one_minus_alphas_bar_sqrt, n_steps)
-        out = engine.sample_chains(self.members, xf, y0hats, mus, coef, draws, noise=noise, seed=seed or 0,
-                                   member_ids=self.member_ids, image_offset=image_offset, images_total=images_total,
-                                   draw_offset=draw_offset, draws_total=draws_total, temperature=temperature)
         n = xf.shape[1]
-        return EnsembleResult(out["y"], out.get("probs"), (image_offset, image_offset + n))
+        total = images_total if images_total else n
+        # bound the activation workspace (2 x rows x F 16-bit per member): process image tiles in turn;
+        # Philox ids are global, so tiling does not change a single sample
+        tile = max(1, min(n, self.max_rows_per_call // max(1, int(draws))))
+        ys, ps = [], []
+        for lo in range(0, n, tile):
+            hi = min(n, lo + tile)
+            out = engine.sample_chains(
+                self.members, xf[:, lo:hi], y0hats[:, lo:hi], mus[:, lo:hi], coef, draws,
+                noise=None if noise is None else noise[:, :, :, lo:hi], seed=seed or 0, member_ids=self.member_ids,
+                image_offset=image_offset + lo, images_total=max(total, image_offset + n), draw_offset=draw_offset,
+                draws_total=draws_total, temperature=temperature)
+            ys.append(out["y"])
+            ps.append(out.get("probs"))
+        y = ys[0] if len(ys) == 1 else torch.cat(ys, dim=2)
+        p = None if ps[0] is None else (ps[0] if len(ps) == 1 else torch.cat(ps, dim=2))
+        return EnsembleResult(y, p, (image_offset, image_offset + n))
 
 
 def sample_ensemble(models_or_ensemble, x, y0hats, draws, n_steps, alphas, one_minus_alphas_bar_sqrt, *,

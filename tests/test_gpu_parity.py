@@ -93,9 +93,31 @@ def test_tensor_path_matches_operand_rounding_emulation(name):
         assert err <= TOL_EMU * (10 if prec == "bf16" else 1), f"{name}/{prec}: rel err vs emulation {err:.3e}"
 
 
+@pytest.fixture
+def pair_mode():
+    """force cta_group::2 (CTA-pair, 256-row tiles) for the duration of a test"""
+    from nested_diffusion_b200 import engine
+
+    engine.set_option(0, "ctas", 2)
+    yield
+    engine.set_option(0, "ctas", 0)
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
 @pytest.mark.parametrize("F,rows,prec", [(256, 128, "fp16"), (256, 100, "bf16"), (512, 300, "fp16"), (1024, 257, "fp16")])
-def test_single_gemm_layer(F, rows, prec):
-    """ladine_debug_layer: one tcgen05 GEMM + fused epilogue vs torch FP64 on identically rounded operands."""
+def test_single_gemm_layer(F, rows, prec, ctas):
+    """ladine_debug_layer: one tcgen05 GEMM + fused epilogue vs torch FP64 on identically rounded operands,
+    for both tile geometries (cta_group::1 128x256 tiles, cta_group::2 256x256 pair tiles)."""
+    from nested_diffusion_b200 import engine
+
+    engine.set_option(0, "ctas", ctas)
+    try:
+        _single_gemm_layer(F, rows, prec)
+    finally:
+        engine.set_option(0, "ctas", 0)
+
+
+def _single_gemm_layer(F, rows, prec):
     import ctypes as C
 
     from nested_diffusion_b200 import _capi, engine
@@ -106,7 +128,7 @@ def test_single_gemm_layer(F, rows, prec):
     p = orc.fold_member(sd, T, torch.float64)
     dt = ODT[prec]
     g = torch.Generator().manual_seed(1)
-    rows_pad = (rows + 127) // 128 * 128
+    rows_pad = (rows + 255) // 256 * 256
     h_in = torch.zeros(rows_pad, pm.Fp, dtype=dt)
     h_in[:rows, :F] = (torch.rand(rows, F, generator=g) * 2).to(dt)
     lib, h = _capi.load(), _capi.handle(0)
@@ -132,6 +154,41 @@ def test_single_gemm_layer(F, rows, prec):
     want_eps = h3 @ p["W4"].T
     got_eps = part[:rows, :, :Cc].double().sum(dim=1).cpu()
     assert (got_eps - want_eps).abs().max() <= 2e-5 * max(1.0, float(want_eps.abs().max()))
+
+
+@pytest.mark.parametrize("name", ["tc_f256_t200", "tc_f512_t100"])
+def test_pair_mode_chain_matches_reference_golden(name, pair_mode):
+    test_chain_matches_reference_golden(name)
+    test_tensor_path_matches_operand_rounding_emulation(name)
+
+
+def test_pair_mode_equals_single_mode_bitwise():
+    """The two tile geometries accumulate every output element over K in the same order -> identical bits."""
+    import nested_diffusion_b200 as nd
+    from nested_diffusion_b200 import engine
+    from nested_diffusion_b200.schedule import coef_table
+
+    T, N, D, K, Cc, F = 15, 70, 5, 3, 2, 512
+    sds = [orc.synth_state_dict(400 + k, F, 16, 16, Cc, T) for k in range(K)]
+    pms = [nd.PackedMember({k: v.cuda() for k, v in sd.items()}, n_steps=T, precision="fp16") for sd in sds]
+    g = torch.Generator().manual_seed(9)
+    xf = torch.randn(K, N, F, generator=g).cuda()
+    yh = torch.softmax(torch.randn(K, N, Cc, generator=g), -1).cuda()
+    alphas, omabs = orc.schedule_tensors(orc.make_beta_schedule("linear", T, 1e-4, 0.02))
+    coef = coef_table(alphas, omabs, T)
+    outs = {}
+    for ctas, lanes in ((1, 1), (2, 1), (1, 2), (2, 3)):
+        engine.set_option(0, "ctas", ctas)
+        engine.set_option(0, "lanes", lanes)
+        try:
+            outs[(ctas, lanes)] = engine.sample_chains(pms, xf, yh, yh, coef, D, seed=5)["y"].clone()
+        finally:
+            engine.set_option(0, "ctas", 0)
+            engine.set_option(0, "lanes", 1)
+    ref = outs[(1, 1)]
+    assert torch.isfinite(ref).all()
+    for key, val in outs.items():
+        assert torch.equal(ref, val), key
 
 
 def test_philox_equals_injected_replay_and_is_deterministic():

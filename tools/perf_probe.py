@@ -8,6 +8,12 @@ from nested_diffusion_b200.schedule import coef_table, make_beta_schedule, sched
 
 K, N, D, F, T = (int(v) for v in sys.argv[1:6])
 prec = sys.argv[6] if len(sys.argv) > 6 else "auto"
+lanes = int(sys.argv[7]) if len(sys.argv) > 7 else 2
+engine.set_option(0, "lanes", lanes)
+ctas = int(sys.argv[8]) if len(sys.argv) > 8 else 0
+engine.set_option(0, "ctas", ctas)
+pdl = int(sys.argv[9]) if len(sys.argv) > 9 else 1
+engine.set_option(0, "pdl", pdl)
 C = 2
 dev = torch.device("cuda")
 g = torch.Generator(device="cuda").manual_seed(0)
@@ -32,7 +38,9 @@ xf = torch.randn(K, N, F, device=dev, generator=g)
 yh = torch.softmax(torch.randn(K, N, C, device=dev, generator=g), -1)
 alphas, omabs = schedule_tensors(make_beta_schedule("linear", T, 1e-4, 0.02))
 coef = coef_table(alphas, omabs, T)
-for it in range(3):
+for it in range(4):
+    if it == 3:
+        engine.set_profiling(0, True)
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     e0.record()
@@ -43,4 +51,5 @@ for it in range(3):
     flops = K * N * D * T * (4.0 * F * F + 6 * F * C)
     print(f"K={K} N={N} D={D} F={F} T={T} {members[0].precision}: {ms:.2f} ms  ({ms/T*1e3:.1f} us/step)  "
           f"{flops/ms/1e9:.1f} TFLOP/s  samples/s(T=1000 equiv)={K*N*D/(ms/1e3)*T/1000:.0f}  host enqueue {1e3*(t1-t0):.1f} ms  "
-          f"finite={bool(torch.isfinite(y).all())} launches={engine.last_launches(0)}")
+          f"finite={bool(torch.isfinite(y).all())} launches={engine.last_launches(0)} lanes={lanes} ctas={ctas} pdl={pdl}")
+print("profile:", engine.get_profile(0))
