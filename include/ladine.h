@@ -158,9 +158,10 @@ int ladine_set_profiling(ladine_handle* h, int enabled);
 int ladine_get_profile(ladine_handle* h, float ms_out[4], int64_t count_out[3]);
 
 /* Debug/test entry: one trunk GEMM layer (2 or 3) of `member` at table index t on `rows` rows.
- * h_in  : [rows_pad, Fpad] 16-bit operands in the member's operand type (rows_pad = rows rounded up to 128)
+ * h_in  : [rows_pad, Fpad] 16-bit operands in the member's operand type (rows_pad = rows rounded up to 256)
  * h_out : layer 2 -> [rows_pad, Fpad] 16-bit activations; layer 3 -> unused (may be NULL)
- * part  : layer 3 -> [rows_pad, Fpad/256, Cpad] FP32 partial lin4 sums; layer 2 -> unused. */
+ * part  : layer 3 -> [rows_pad, Fpad/256, 2, Cpad] FP32 partial lin4 sums (one per 128 columns); layer 2 -> unused.
+ * Uses (and may grow) the handle's workspace: do not overlap with an in-flight ladine_sample on the handle. */
 int ladine_debug_layer(ladine_handle* h, const ladine_member* member, int layer, int t, const void* h_in,
                        int rows, void* h_out, float* part, void* stream);
 /* padded feature dim and padded class count used by the packed layout */

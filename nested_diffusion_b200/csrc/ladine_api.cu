@@ -463,11 +463,12 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
   const uint64_t lane_base = off;
   uint64_t lo = 0;
   const uint64_t o_u = lo; lo = align_up(lo + (uint64_t)gmax * a->N * Fp * 4, 1024);
-  uint64_t o_h1 = 0, o_h2 = 0, o_part = 0, o_y = 0;
+  uint64_t o_h1 = 0, o_h2 = 0, o_part = 0, o_y = 0, o_sched = 0;
   if (tensor) {
     o_h1 = lo; lo = align_up(lo + m_total * Fp * 2, 1024);
     o_h2 = lo; lo = align_up(lo + m_total * Fp * 2, 1024);
-    o_part = lo; lo = align_up(lo + m_total * (Fp / 256) * Cp * 4, 1024);
+    o_part = lo; lo = align_up(lo + m_total * (Fp / 256) * 2 * Cp * 4, 1024);
+    o_sched = lo; lo = align_up(lo + sched_bytes_bound(gmax, rows, Fp / 256), 1024);
     o_y = lo; lo = align_up(lo + 2 * m_total * Cp * 4, 1024);
   }
   const uint64_t lane_bytes = lo;
@@ -534,6 +535,7 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
         tw.part = reinterpret_cast<float*>(lw + o_part);
         tw.ybuf = reinterpret_cast<float*>(lw + o_y);
         tw.u = d_u;
+        tw.sched = reinterpret_cast<int32_t*>(lw + o_sched);
         std::string err;
         chains[l] = tensor_chain_create(h, members + k0, g, ids, h_coef, tw, si.n_slots, si.n_traj, ls,
                                         &h->last_launches, &err, &e);
@@ -666,8 +668,11 @@ int ladine_debug_layer(ladine_handle* h, const ladine_member* member, int layer,
   if (member->precision == LADINE_PREC_FP32) return fail(h, LADINE_ERR_UNSUPPORTED, "debug layer is for the tensor path");
   if ((layer == 2 && !h_out) || (layer == 3 && !part)) return fail(h, LADINE_ERR_INVALID, "missing output buffer");
   DeviceGuard guard(h->device);
+  int rc = ensure_workspace(h, sched_bytes_bound(1, rows, member->Fp / 256));
+  if (rc != LADINE_OK) return rc;
   std::string err;
-  cudaError_t e = launch_debug_layer(h, member, layer, t, h_in, rows, h_out, part, static_cast<cudaStream_t>(stream), &err);
+  cudaError_t e = launch_debug_layer(h, member, layer, t, h_in, rows, h_out, part, static_cast<int32_t*>(h->ws),
+                                     static_cast<cudaStream_t>(stream), &err);
   if (e != cudaSuccess) {
     if (!err.empty()) return fail(h, LADINE_ERR_CUDA, err);
     return fail_cuda(h, e, "debug layer launch");

@@ -49,7 +49,7 @@ struct ladine_handle {
   static constexpr int kMaxLanes = 4;
   int lanes = 1;
   int ctas = 0;             // 0 = choose per call, 1 = cta_group::1, 2 = cta_group::2 CTA pairs
-  double pair_gain = 1.06;   // measured throughput ratio pair/single per useful tile (see choose_ctas)
+  double pair_gain = 1.08;   // measured throughput ratio pair/single per useful tile (see choose_ctas)
   cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};  // [0] unused: caller's stream
   cudaEvent_t ev_fork = nullptr;
   cudaEvent_t ev_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
@@ -79,9 +79,10 @@ size_t resident_smem_bytes(int Fp, int Cp);
 struct TensorWorkspace {
   void* h1;      // [K * rows_pad, Fp] 16-bit
   void* h2;      // [K * rows_pad, Fp] 16-bit
-  float* part;   // [K * rows_pad, Fp / 256, Cp]
+  float* part;   // [K * rows_pad, Fp / 256, 2, Cp]  (one lin4 partial per 128-column slot)
   float* ybuf;   // 2 x [K * rows_pad, Cp] (ping-pong chain state)
   float* u;      // [K, N, Fp]
+  int32_t* sched;  // static tile schedule of this lane's GEMM launches
 };
 struct TensorChain;  // one lane: a group of members advancing through the reverse steps on one stream
 TensorChain* tensor_chain_create(ladine_handle* h, const ladine_member* const* members, const ladine_sample_args& a,
@@ -90,7 +91,8 @@ TensorChain* tensor_chain_create(ladine_handle* h, const ladine_member* const* m
 cudaError_t tensor_chain_step(TensorChain* c, int t, int64_t* launches);
 void tensor_chain_destroy(TensorChain* c);
 cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int layer, int t, const void* h_in, int rows,
-                               void* h_out, float* part, cudaStream_t st, std::string* err);
+                               void* h_out, float* part, int32_t* sched_buf, cudaStream_t st, std::string* err);
+size_t sched_bytes_bound(int K, int rows, int NB);
 size_t tensor_gemm_smem_bytes(int Cp);
 void set_use_pdl(bool on);
 

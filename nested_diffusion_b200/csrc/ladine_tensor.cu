@@ -140,11 +140,22 @@ struct GemmParams {
   void* h_out;                         // layer 2: [M_total, Fp] 16-bit
   float* part;                         // layer 3: [M_total, NB, Cp]
   int Fp, NB, KB;                      // padded feature dim, N tiles (Fp/256), K blocks (Fp/64)
-  int mblk;                            // row tiles (128 * CTAS rows each) per member
   int rows;                            // valid rows per member
-  int rows_pad;                        // mblk * 128 * CTAS
-  int num_tiles;                       // K * mblk * NB
-  uint32_t idesc;
+  int rows_pad;                        // row stride between members (multiple of 128 * CTAS)
+  // static tile schedule: unit u (a CTA, or a CTA pair) runs sched[u * sched_stride + 0, 1, ...] until a -1.
+  // entry = member << 23 | nb << 13 | mb << 1 | half   (half: CTA-pair tile of 2 x 64 rows, M=128 MMAs)
+  const int32_t* sched;
+  int sched_stride;
+  uint32_t idesc;                      // full tiles: M = 128 * CTAS
+  uint32_t idesc_half;                 // pair half tiles: M = 128 (64 rows per CTA)
+};
+
+struct TileCode {
+  int member, nb, mb, half;
+  __host__ __device__ static int32_t pack(int member, int nb, int mb, int half) {
+    return (int32_t)((member << 23) | (nb << 13) | (mb << 1) | half);
+  }
+  __device__ explicit TileCode(int32_t c) : member(c >> 23), nb((c >> 13) & 1023), mb((c >> 1) & 4095), half(c & 1) {}
 };
 
 // pipeline geometry per CTA: CTAS = 1 -> A 128x64 + B 256x64 per stage; CTAS = 2 (cta_group::2, the
@@ -251,7 +262,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;   // position in the CTA pair; 0 issues the MMAs
   const int unit = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // tile-scheduling unit (CTA or pair)
-  const int n_units = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -279,20 +289,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
   pdl_launch_dependents();  // the next kernel's CTAs can take this SM the moment this CTA retires
   pdl_wait();               // everything below reads/writes buffers shared with the previous kernels
 
-  const int tiles_per_member = p.mblk * p.NB;
+  const int32_t* my_sched = p.sched + (size_t)unit * p.sched_stride;
 
   if (warp == 0) {
     // ===================== TMA producer (one per CTA) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = unit; tile < p.num_tiles; tile += n_units) {
-        const int member = tile / tiles_per_member;
-        const int rem = tile - member * tiles_per_member;
-        const int nb = rem / p.mblk, mb = rem - nb * p.mblk;
-        const int arow = member * p.rows_pad + mb * (BM * CTAS) + (int)rank * BM;
-        const int brow = nb * BN + (int)rank * Cfg::kBRows;
-        const CUtensorMap* tb = &p.tmB[member];
+      for (int it = 0;; ++it) {
+        const int32_t code = __ldg(my_sched + it);
+        if (code < 0) break;
+        const TileCode tc(code);
+        // a half tile gives each CTA of the pair 64 rows; the 128-row box is still loaded (upper half unused)
+        const int arow = tc.member * p.rows_pad + tc.mb * (BM * CTAS) + (int)rank * (tc.half ? BM / 2 : BM);
+        const int brow = tc.nb * BN + (int)rank * Cfg::kBRows;
+        const CUtensorMap* tb = &p.tmB[tc.member];
         for (int kb = 0; kb < p.KB; ++kb) {
           mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u, 0);
           const uint32_t fb = smem_u32(&bars->full[stage]);
@@ -315,8 +326,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
     if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = unit; tile < p.num_tiles; tile += n_units, ++it) {
+      for (int it = 0;; ++it) {
+        const int32_t code = __ldg(my_sched + it);
+        if (code < 0) break;
+        const uint32_t idesc = (code & 1) ? p.idesc_half : p.idesc;
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(smem_u32(&bars->acc_empty[as]), aphase ^ 1u, 1);
@@ -331,9 +344,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
           for (int k4 = 0; k4 < BK / UK; ++k4) {
             // +32 bytes per K=16 slice inside the 128-byte swizzle row: +2 in the >>4 address field
             if (CTAS == 2)
-              umma_f16_pair(d_tmem, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), p.idesc, (uint32_t)((kb | k4) != 0));
+              umma_f16_pair(d_tmem, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), idesc, (uint32_t)((kb | k4) != 0));
             else
-              umma_f16(d_tmem, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), p.idesc, (uint32_t)((kb | k4) != 0));
+              umma_f16(d_tmem, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), idesc, (uint32_t)((kb | k4) != 0));
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
           if (CTAS == 2) umma_commit_pair(smem_u32(&bars->empty[stage]));
@@ -346,18 +359,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5), this CTA's 128 rows x 256 columns =====================
+    // ===================== epilogue (warps 2..5), this CTA's rows x 256 columns =====================
     const int et = threadIdx.x - 64;         // 0..127
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
-    const int row_in_tile = quad * 32 + lane;
     float* sScale = sEpi;
     float* sShift = sEpi + BN;
     float* sW4 = sEpi + 2 * BN;              // [CP][BN]
-    int it = 0;
-    for (int tile = unit; tile < p.num_tiles; tile += n_units, ++it) {
-      const int member = tile / tiles_per_member;
-      const int rem = tile - member * tiles_per_member;
-      const int nb = rem / p.mblk, mb = rem - nb * p.mblk;
+    for (int it = 0;; ++it) {
+      const int32_t code = __ldg(my_sched + it);
+      if (code < 0) break;
+      const TileCode tc(code);
+      const int member = tc.member, nb = tc.nb;
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       // stage this tile's per-column parameters (independent of the accumulator: issued before the wait)
@@ -389,55 +401,75 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
       mbar_wait(smem_u32(&bars->acc_full[as]), aphase, 3);
       tc_fence_after();
 
-      const int row_m = mb * (BM * CTAS) + (int)rank * BM + row_in_tile;   // row within the member
+      // Accumulator layout (TMEM lane = datapath):
+      //   full tile : lane l <-> row l of this CTA's 128 rows, TMEM columns 0..255 <-> output columns 0..255
+      //   half tile : this CTA owns 64 rows; lanes 0..63 hold columns 0..127, lanes 64..127 columns 128..255
+      //               of rows (lane & 63), both in TMEM columns 0..127 (the UMMA 2-SM M=128 "2x2" layout)
+      const bool half = CTAS == 2 && tc.half;
+      const int row_m = half ? tc.mb * (BM * CTAS) + (int)rank * (BM / 2) + (quad & 1) * 32 + lane
+                             : tc.mb * (BM * CTAS) + (int)rank * BM + quad * 32 + lane;   // row within the member
       const bool valid = row_m < p.rows;
       const size_t grow = (size_t)member * p.rows_pad + row_m;
       const uint32_t taddr = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quad * 32) << 16);
-      float eacc[LAYER == 3 ? CP : 1];
-#pragma unroll
-      for (int c = 0; c < (LAYER == 3 ? CP : 1); ++c) eacc[c] = 0.f;
-
+      // lin4 partials are kept per 128-column slot so that every tile geometry sums the same values in the
+      // same order (tail kernel: fixed-order sum over 2 * NB slots) -> results do not depend on the geometry
+      const int nslot = half ? 1 : 2;
+      const int slot0 = half ? (quad >> 1) : 0;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)(ch * 32), v);
-        tmem_ld_wait();
-        float hcol[32];
+      for (int sl = 0; sl < nslot; ++sl) {
+        const int slot = slot0 + sl;
+        float eacc[LAYER == 3 ? CP : 1];
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 sc = *reinterpret_cast<const float4*>(sScale + ch * 32 + j4 * 4);
-          const float4 sh = *reinterpret_cast<const float4*>(sShift + ch * 32 + j4 * 4);
-          hcol[4 * j4 + 0] = softplus_log2dom(fmaf(sc.x, __uint_as_float(v[4 * j4 + 0]), sh.x));
-          hcol[4 * j4 + 1] = softplus_log2dom(fmaf(sc.y, __uint_as_float(v[4 * j4 + 1]), sh.y));
-          hcol[4 * j4 + 2] = softplus_log2dom(fmaf(sc.z, __uint_as_float(v[4 * j4 + 2]), sh.z));
-          hcol[4 * j4 + 3] = softplus_log2dom(fmaf(sc.w, __uint_as_float(v[4 * j4 + 3]), sh.w));
+        for (int c = 0; c < (LAYER == 3 ? CP : 1); ++c) eacc[c] = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          const int ocol = slot * 128 + ch * 32;                      // output column within the tile
+          const uint32_t tcol = (uint32_t)((half ? 0 : sl * 128) + ch * 32);  // TMEM column within the stage
+          uint32_t v[32];
+          tmem_ld32(taddr + tcol, v);
+          tmem_ld_wait();
+          float hcol[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 sc = *reinterpret_cast<const float4*>(sScale + ocol + j4 * 4);
+            const float4 sh = *reinterpret_cast<const float4*>(sShift + ocol + j4 * 4);
+            hcol[4 * j4 + 0] = softplus_log2dom(fmaf(sc.x, __uint_as_float(v[4 * j4 + 0]), sh.x));
+            hcol[4 * j4 + 1] = softplus_log2dom(fmaf(sc.y, __uint_as_float(v[4 * j4 + 1]), sh.y));
+            hcol[4 * j4 + 2] = softplus_log2dom(fmaf(sc.z, __uint_as_float(v[4 * j4 + 2]), sh.z));
+            hcol[4 * j4 + 3] = softplus_log2dom(fmaf(sc.w, __uint_as_float(v[4 * j4 + 3]), sh.w));
+          }
+          if (LAYER == 2) {
+            if (valid) {
+              // 32 consecutive 16-bit outputs of this row = 64 B = two full 32-byte sectors: 256-bit stores
+              T16* dst = reinterpret_cast<T16*>(p.h_out) + grow * p.Fp + nb * BN + ocol;
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                uint32_t o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = Pack16<T16>::pack(hcol[16 * q + 2 * i], hcol[16 * q + 2 * i + 1]);
+                st_global_256(dst + 16 * q, o);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+              float e = eacc[c];
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 w = *reinterpret_cast<const float4*>(sW4 + c * BN + ocol + j4 * 4);
+                e = fmaf(hcol[4 * j4 + 0], w.x, e);
+                e = fmaf(hcol[4 * j4 + 1], w.y, e);
+                e = fmaf(hcol[4 * j4 + 2], w.z, e);
+                e = fmaf(hcol[4 * j4 + 3], w.w, e);
+              }
+              eacc[c] = e;
+            }
+          }
         }
-        if (LAYER == 2) {
-          if (valid) {
-            // 32 consecutive 16-bit outputs of this row = 64 B = two full 32-byte sectors: 256-bit stores
-            T16* dst = reinterpret_cast<T16*>(p.h_out) + grow * p.Fp + nb * BN + ch * 32;
+        if (LAYER == 3 && valid) {
+          float* dst = p.part + ((grow * p.NB + nb) * 2 + slot) * CP;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              uint32_t o[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = Pack16<T16>::pack(hcol[16 * q + 2 * i], hcol[16 * q + 2 * i + 1]);
-              st_global_256(dst + 16 * q, o);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < CP; ++c) {
-            float e = eacc[c];
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 w = *reinterpret_cast<const float4*>(sW4 + c * BN + ch * 32 + j4 * 4);
-              e = fmaf(hcol[4 * j4 + 0], w.x, e);
-              e = fmaf(hcol[4 * j4 + 1], w.y, e);
-              e = fmaf(hcol[4 * j4 + 2], w.z, e);
-              e = fmaf(hcol[4 * j4 + 3], w.w, e);
-            }
-            eacc[c] = e;
-          }
+          for (int c = 0; c < CP; ++c) dst[c] = eacc[c];
         }
       }
       // accumulator stage drained: hand it back to the MMA issuer (in the leader CTA)
@@ -447,11 +479,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
         const uint32_t eb = smem_u32(&bars->acc_empty[as]);
         if (CTAS == 2) mbar_arrive_cluster(mapa_rank(eb, 0));
         else mbar_arrive(eb);
-      }
-      if (LAYER == 3 && valid) {
-        float* dst = p.part + (grow * p.NB + nb) * CP;
-#pragma unroll
-        for (int c = 0; c < CP; ++c) dst[c] = eacc[c];
       }
     }
   }
@@ -532,8 +559,8 @@ __global__ void __launch_bounds__(kTailThreads) tailhead_kernel(const __grid_con
       }
     } else {
       float eps = __ldg(p.b4[k] + c);
-      const float* pp = p.part + (grow * p.NB) * CP + c;
-      for (int nb = 0; nb < p.NB; ++nb) eps += pp[nb * CP];  // fixed order: deterministic
+      const float* pp = p.part + (grow * p.NB) * 2 * CP + c;
+      for (int sl = 0; sl < 2 * p.NB; ++sl) eps += pp[sl * CP];  // fixed order over 128-column slots: deterministic
       const float y = p.y_prev[grow * CP + c];
       if (p.t > 0) {
         const float z = p.noise ? __ldg(p.noise + ((((size_t)k * p.D + d) * p.n_slots + p.slot) * p.N + n) * C + c)
@@ -700,12 +727,6 @@ cudaError_t launch_gemm_t(const GemmParams& p, int grid, cudaStream_t st) {
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
-// grid size for a GEMM launch: one CTA (or CTA pair) per tile-scheduling unit, at most one per SM
-int gemm_grid(const ladine_handle* h, int num_tiles, int ctas) {
-  const int units = h->sm_count / ctas;
-  return (num_tiles < units ? num_tiles : units) * ctas;
-}
-
 template <int LAYER, typename T16>
 cudaError_t launch_gemm_c(const GemmParams& p, int grid, int Cp, int ctas, cudaStream_t st) {
   if (LAYER == 2) {  // the layer-2 epilogue does not depend on the class count
@@ -805,11 +826,83 @@ size_t tensor_gemm_smem_bytes(int Cp) {
 // B-operand shared-memory/L2 traffic per SM but pad each member's rows to a multiple of 256.
 void set_use_pdl(bool on) { g_use_pdl = on; }
 
+// ------------------------------------------------------------------------------------------
+// static tile schedule
+// ------------------------------------------------------------------------------------------
+struct TilePlan {
+  int ctas = 1;
+  int tile_rows = BM;      // rows per full tile (128 * ctas)
+  int n_full = 0;          // full row tiles per member
+  int has_half = 0;        // pair mode: the member's last <= 128 rows run as a half tile (2 x 64 rows, M=128 MMAs)
+  int rows_pad = 0;        // row stride between members
+  int units = 0;           // CTAs (ctas == 1) or CTA pairs (ctas == 2) that get work
+  int stride = 0;          // table row length (entries per unit incl. the -1 terminator)
+  std::vector<int32_t> table;
+};
+
+// Tiles in canonical order (member, N tile, row tile: the row tiles sharing a W tile are adjacent, so they
+// run concurrently and the W tile is fetched from HBM once).  Costs: full = 20, half = 17 -- measured: the
+// mainloop is bound by the 128 B/clk shared-memory port (TMA writes + UMMA operand reads), and a half tile
+// moves 72 KB per K block against 80 KB for a full pair tile, so it is only ~15 % cheaper although it does
+// half the math.  Per-unit quotas come from longest-processing-time assignment; the canonical sequence is
+// then dealt to the least-loaded unit that still has quota for that tile kind, which keeps neighbours in time.
+TilePlan plan_tiles(int K, int rows, int NB, int ctas, int max_units) {
+  TilePlan tp;
+  tp.ctas = ctas;
+  tp.tile_rows = BM * ctas;
+  tp.n_full = rows / tp.tile_rows;
+  const int rem = rows - tp.n_full * tp.tile_rows;
+  tp.has_half = (ctas == 2 && rem > 0 && rem <= BM) ? 1 : 0;
+  if (rem > 0 && !tp.has_half) tp.n_full += 1;
+  tp.rows_pad = (tp.n_full + tp.has_half) * tp.tile_rows;
+  const int n_items = K * NB * (tp.n_full + tp.has_half);
+  tp.units = n_items < max_units ? n_items : max_units;
+  const int U = tp.units;
+  // LPT quotas
+  std::vector<int> load(U, 0), qfull(U, 0), qhalf(U, 0);
+  auto least = [&](const std::vector<int>& need) {
+    int best = -1;
+    for (int u = 0; u < U; ++u)
+      if (need.empty() || need[u] > 0)
+        if (best < 0 || load[u] < load[best]) best = u;
+    return best;
+  };
+  const std::vector<int> none;
+  constexpr int kCostFull = 20, kCostHalf = 17;
+  for (int i = 0; i < K * NB * tp.n_full; ++i) { const int u = least(none); load[u] += kCostFull; qfull[u] += 1; }
+  for (int i = 0; i < K * NB * tp.has_half; ++i) { const int u = least(none); load[u] += kCostHalf; qhalf[u] += 1; }
+  int longest = 0;
+  for (int u = 0; u < U; ++u) longest = (qfull[u] + qhalf[u]) > longest ? (qfull[u] + qhalf[u]) : longest;
+  tp.stride = longest + 1;
+  tp.table.assign((size_t)U * tp.stride, -1);
+  std::vector<int> fill(U, 0);
+  std::fill(load.begin(), load.end(), 0);
+  for (int k = 0; k < K; ++k)
+    for (int nb = 0; nb < NB; ++nb)
+      for (int mb = 0; mb < tp.n_full + tp.has_half; ++mb) {
+        const int half = (tp.has_half && mb == tp.n_full) ? 1 : 0;
+        const int u = least(half ? qhalf : qfull);
+        (half ? qhalf : qfull)[u] -= 1;
+        load[u] += half ? kCostHalf : kCostFull;
+        tp.table[(size_t)u * tp.stride + fill[u]++] = TileCode::pack(k, nb, mb, half);
+      }
+  return tp;
+}
+
+size_t sched_bytes_bound(int K, int rows, int NB) {
+  // generous bound for either geometry: every unit's row is at most ceil(items / units) + 2 entries long
+  const size_t items = (size_t)K * NB * ((rows + BM - 1) / BM + 1);
+  return (items + 148 * 4) * sizeof(int32_t) * 2;
+}
+
 int choose_ctas(const ladine_handle* h, int rows) {
   if (h->ctas == 1 || h->ctas == 2) return h->ctas;
-  const double eff1 = (double)rows / (((rows + 127) / 128) * 128);
-  const double eff2 = (double)rows / (((rows + 255) / 256) * 256);
-  return eff2 * h->pair_gain > eff1 ? 2 : 1;
+  // cost in single-CTA 128-row tile times; a full pair tile (256 rows on 2 SMs) costs 2 / pair_gain, a half
+  // tile 1.7 / pair_gain (see plan_tiles).  Pairs must win by 3 % to be chosen (static-schedule quantisation).
+  const int full2 = rows / 256, rem2 = rows - full2 * 256;
+  const double cost2 = (2.0 * full2 + (rem2 == 0 ? 0.0 : rem2 <= 128 ? 1.7 : 2.0)) / h->pair_gain;
+  const double cost1 = (rows + 127) / 128;
+  return cost2 * 1.03 < cost1 ? 2 : 1;
 }
 
 // One lane = one group of members advancing through the reverse steps on its own stream.  Lanes are
@@ -851,12 +944,18 @@ struct TensorChain {
     K = a.K;
     const int rows = a.N * a.D;
     ctas = choose_ctas(h, rows);
-    const int tile_rows = BM * ctas;
-    const int mblk = (rows + tile_rows - 1) / tile_rows;
-    const int rows_pad = mblk * tile_rows;
+    const int NBt = Fp / BN;
+    if ((rows + BM - 1) / BM > 4096 || NBt > 1024) {
+      *err = "too many rows per member for one launch group (max 524288 chains): tile the images (NestedEnsemble does)";
+      return cudaErrorInvalidValue;
+    }
+    const TilePlan plan = plan_tiles(K, rows, NBt, ctas, h->sm_count / ctas);
+    const int rows_pad = plan.rows_pad;
     const size_t m_total = (size_t)K * rows_pad;
 
     cudaError_t e = resolve_encode(h, err);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(ws.sched, plan.table.data(), plan.table.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
     if (!make_tmap(h, &g2.tmA, ws.h1, m_total, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
     if (!make_tmap(h, &g3.tmA, ws.h2, m_total, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
@@ -867,17 +966,18 @@ struct TensorChain {
     }
     for (GemmParams* g : {&g2, &g3}) {
       g->Fp = Fp;
-      g->NB = Fp / BN;
+      g->NB = NBt;
       g->KB = Fp / BK;
-      g->mblk = mblk;
       g->rows = rows;
       g->rows_pad = rows_pad;
-      g->num_tiles = K * mblk * (Fp / BN);
+      g->sched = ws.sched;
+      g->sched_stride = plan.stride;
       g->idesc = make_idesc(bf16, ctas);
+      g->idesc_half = make_idesc(bf16, 1);  // M = 128 across the pair
     }
     g2.h_out = ws.h2;
     g3.part = ws.part;
-    grid = gemm_grid(h, g2.num_tiles, ctas);
+    grid = plan.units * ctas;
 
     for (int k = 0; k < K; ++k) {
       tp.W1y[k] = members[k]->W1y;
@@ -983,16 +1083,17 @@ cudaError_t tensor_chain_step(TensorChain* c, int t, int64_t* launches) { return
 void tensor_chain_destroy(TensorChain* c) { delete c; }
 
 cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int layer, int t, const void* h_in, int rows,
-                               void* h_out, float* part, cudaStream_t st, std::string* err) {
+                               void* h_out, float* part, int32_t* sched_buf, cudaStream_t st, std::string* err) {
   const bool bf16 = m->precision == LADINE_PREC_BF16;
   cudaError_t e = resolve_encode(h, err);
   if (e != cudaSuccess) return e;
   const int Fp = m->Fp;
-  const int ctas = (h->ctas == 2) ? 2 : 1;  // debug entry: caller-provided buffers are padded to 128 rows unless "ctas"=2
-  const int tile_rows = BM * ctas;
-  const int mblk = (rows + tile_rows - 1) / tile_rows;
+  const int ctas = (h->ctas == 2) ? 2 : 1;  // debug entry: "ctas" = 2 exercises the CTA-pair geometry (incl. half tiles)
+  const TilePlan plan = plan_tiles(1, rows, Fp / BN, ctas, h->sm_count / ctas);
+  e = cudaMemcpyAsync(sched_buf, plan.table.data(), plan.table.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
   GemmParams g{};
-  if (!make_tmap(h, &g.tmA, h_in, (uint64_t)mblk * tile_rows, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
+  if (!make_tmap(h, &g.tmA, h_in, (uint64_t)plan.rows_pad, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
   if (!make_tmap(h, &g.tmB[0], layer == 2 ? m->W2h : m->W3h, Fp, Fp, BN / ctas, bf16, err)) return cudaErrorInvalidValue;
   g.scale[0] = m->A[layer - 1] + (size_t)t * Fp;
   g.shift[0] = m->Cc[layer - 1] + (size_t)t * Fp;
@@ -1002,12 +1103,13 @@ cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int lay
   g.Fp = Fp;
   g.NB = Fp / BN;
   g.KB = Fp / BK;
-  g.mblk = mblk;
   g.rows = rows;
-  g.rows_pad = mblk * tile_rows;
-  g.num_tiles = mblk * g.NB;
+  g.rows_pad = plan.rows_pad;
+  g.sched = sched_buf;
+  g.sched_stride = plan.stride;
   g.idesc = make_idesc(bf16, ctas);
-  const int grid = gemm_grid(h, g.num_tiles, ctas);
+  g.idesc_half = make_idesc(bf16, 1);
+  const int grid = plan.units * ctas;
   return layer == 2 ? launch_gemm<2>(g, grid, bf16, m->Cp, ctas, st) : launch_gemm<3>(g, grid, bf16, m->Cp, ctas, st);
 }
 

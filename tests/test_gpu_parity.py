@@ -104,7 +104,8 @@ def pair_mode():
 
 
 @pytest.mark.parametrize("ctas", [1, 2])
-@pytest.mark.parametrize("F,rows,prec", [(256, 128, "fp16"), (256, 100, "bf16"), (512, 300, "fp16"), (1024, 257, "fp16")])
+@pytest.mark.parametrize("F,rows,prec", [(256, 128, "fp16"), (256, 100, "bf16"), (512, 300, "fp16"), (1024, 257, "fp16"),
+                                         (512, 640, "fp16"), (256, 1400, "fp16")])
 def test_single_gemm_layer(F, rows, prec, ctas):
     """ladine_debug_layer: one tcgen05 GEMM + fused epilogue vs torch FP64 on identically rounded operands,
     for both tile geometries (cta_group::1 128x256 tiles, cta_group::2 256x256 pair tiles)."""
@@ -146,13 +147,13 @@ def _single_gemm_layer(F, rows, prec):
     assert ((got - want).abs() <= ulp * want.abs() + 1e-6).all(), float(((got - want).abs() / (want.abs() + 1e-6)).max())
     # layer 3 (+ fused lin4 partials)
     NB = pm.Fp // 256
-    part = torch.zeros(rows_pad, NB, pm.Cp, device="cuda")
+    part = torch.zeros(rows_pad, NB, 2, pm.Cp, device="cuda")
     _capi.check(h, lib.ladine_debug_layer(h, pm.ptr, 3, t, hin_g.data_ptr(), rows, None, part.data_ptr(), stream))
     torch.cuda.synchronize()
     W3 = p["W3"].to(dt).double()
     h3 = torch.nn.functional.softplus(p["A3"][t] * (h_in[:rows, :F].double() @ W3.T) + p["C3"][t])
     want_eps = h3 @ p["W4"].T
-    got_eps = part[:rows, :, :Cc].double().sum(dim=1).cpu()
+    got_eps = part[:rows, :, :, :Cc].double().sum(dim=(1, 2)).cpu()
     assert (got_eps - want_eps).abs().max() <= 2e-5 * max(1.0, float(want_eps.abs().max()))
 
 
