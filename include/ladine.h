@@ -143,9 +143,13 @@ int ladine_fill_noise(ladine_handle* h, const ladine_sample_args* args, int32_t 
 int64_t ladine_last_launches(const ladine_handle* h);
 uint64_t ladine_workspace_bytes(const ladine_handle* h);
 
-/* Tuning knobs.  "lanes" (1..4, default 2): how many groups of members the tensor-core path advances
- * concurrently on internal streams (forked from / joined to the caller's stream), so one group's
- * tail/head kernel and kernel boundaries hide under another group's GEMMs. */
+/* Tuning knobs (tensor-core path).
+ *   "lanes" (1..4, default 1): groups of members advanced concurrently on internal streams (forked from /
+ *       joined to the caller's stream) so one group's tail/head kernel hides under another group's GEMMs;
+ *   "ctas" (0 auto | 1 | 2): GEMM tile geometry -- single CTAs (cta_group::1, 128x256 tiles) or CTA pairs
+ *       (cta_group::2, 256x256 tiles + 2x64-row half tiles); auto picks pairs when the rows pad well;
+ *   "pair_gain_permille": measured per-tile speed ratio pair/single used by the auto choice (default 1080);
+ *   "pdl" (0 default | 1): programmatic dependent launch, applied to single-CTA chains only. */
 int ladine_set_option(ladine_handle* h, const char* key, int64_t value);
 
 /* Optional per-kernel timing of the tensor-core path.  When enabled, ladine_sample brackets every

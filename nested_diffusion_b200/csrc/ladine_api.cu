@@ -570,7 +570,7 @@ int ladine_set_option(ladine_handle* h, const char* key, int64_t value) {
     return LADINE_OK;
   }
   if (strcmp(key, "pdl") == 0) {
-    set_use_pdl(value != 0);
+    h->pdl = value != 0;
     return LADINE_OK;
   }
   if (strcmp(key, "ctas") == 0) {

@@ -48,6 +48,7 @@ struct ladine_handle {
   // lanes: independent member groups run concurrently on internal streams (tensor path)
   static constexpr int kMaxLanes = 4;
   int lanes = 1;
+  bool pdl = false;         // programmatic dependent launch: opt-in, single-CTA chains only (see ladine_tensor.cu)
   int ctas = 0;             // 0 = choose per call, 1 = cta_group::1, 2 = cta_group::2 CTA pairs
   double pair_gain = 1.08;   // measured throughput ratio pair/single per useful tile (see choose_ctas)
   cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};  // [0] unused: caller's stream
@@ -94,7 +95,6 @@ cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int lay
                                void* h_out, float* part, int32_t* sched_buf, cudaStream_t st, std::string* err);
 size_t sched_bytes_bound(int K, int rows, int NB);
 size_t tensor_gemm_smem_bytes(int Cp);
-void set_use_pdl(bool on);
 
 // ---- shared small kernels (ladine_api.cu) ----
 cudaError_t launch_guidance_u(const ladine_member* const* members, int K, int N, const float* y0hat, float* u,

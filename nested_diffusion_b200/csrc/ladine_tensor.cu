@@ -696,10 +696,14 @@ uint32_t make_idesc(bool bf16, int ctas) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * ctas) >> 4) << 24);
 }
 
-bool g_use_pdl = true;  // process-wide; toggled through ladine_set_option("pdl")
+// Programmatic dependent launch is OPT-IN (ladine_set_option("pdl", 1)) and only ever applied to chains of
+// single-CTA kernels: measured neutral on B200 (the chain is bound by the shared-memory port and the power cap,
+// not by launch gaps), and PDL combined with cluster launches (CTA pairs) dead-locked the GPU after a few hundred
+// steps of a 1000-step chain (driver 580.159) -- so a chain that uses pairs never sets the attribute.
+inline bool pdl_allowed(const ladine_handle* h, int ctas) { return h->pdl && ctas == 1; }
 
 template <int LAYER, typename T16, int CP, int CTAS>
-cudaError_t launch_gemm_t(const GemmParams& p, int grid, cudaStream_t st) {
+cudaError_t launch_gemm_t(const GemmParams& p, int grid, bool pdl, cudaStream_t st) {
   const size_t smem = tensor_gemm_smem_bytes(CP);
   auto kern = trunk_gemm_kernel<LAYER, T16, CP, CTAS>;
   // cheap (host-side table update); done per launch so it is right for every device of the process
@@ -713,7 +717,7 @@ cudaError_t launch_gemm_t(const GemmParams& p, int grid, cudaStream_t st) {
   cudaLaunchAttribute attr[2];
   int na = 0;
   attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[na].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  attr[na].val.programmaticStreamSerializationAllowed = (pdl && CTAS == 1) ? 1 : 0;
   ++na;
   if (CTAS == 2) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
@@ -728,13 +732,13 @@ cudaError_t launch_gemm_t(const GemmParams& p, int grid, cudaStream_t st) {
 }
 
 template <int LAYER, typename T16>
-cudaError_t launch_gemm_c(const GemmParams& p, int grid, int Cp, int ctas, cudaStream_t st) {
+cudaError_t launch_gemm_c(const GemmParams& p, int grid, int Cp, int ctas, bool pdl, cudaStream_t st) {
   if (LAYER == 2) {  // the layer-2 epilogue does not depend on the class count
-    return ctas == 2 ? launch_gemm_t<2, T16, 2, 2>(p, grid, st) : launch_gemm_t<2, T16, 2, 1>(p, grid, st);
+    return ctas == 2 ? launch_gemm_t<2, T16, 2, 2>(p, grid, pdl, st) : launch_gemm_t<2, T16, 2, 1>(p, grid, pdl, st);
   }
 #define LADINE_GEMM_CASE(CPV)                                                                          \
   case CPV:                                                                                            \
-    return ctas == 2 ? launch_gemm_t<3, T16, CPV, 2>(p, grid, st) : launch_gemm_t<3, T16, CPV, 1>(p, grid, st);
+    return ctas == 2 ? launch_gemm_t<3, T16, CPV, 2>(p, grid, pdl, st) : launch_gemm_t<3, T16, CPV, 1>(p, grid, pdl, st);
   switch (Cp) {
     LADINE_GEMM_CASE(2)
     LADINE_GEMM_CASE(4)
@@ -746,13 +750,13 @@ cudaError_t launch_gemm_c(const GemmParams& p, int grid, int Cp, int ctas, cudaS
 }
 
 template <int LAYER>
-cudaError_t launch_gemm(const GemmParams& p, int grid, bool bf16, int Cp, int ctas, cudaStream_t st) {
-  return bf16 ? launch_gemm_c<LAYER, __nv_bfloat16>(p, grid, Cp, ctas, st)
-              : launch_gemm_c<LAYER, __half>(p, grid, Cp, ctas, st);
+cudaError_t launch_gemm(const GemmParams& p, int grid, bool bf16, int Cp, int ctas, bool pdl, cudaStream_t st) {
+  return bf16 ? launch_gemm_c<LAYER, __nv_bfloat16>(p, grid, Cp, ctas, pdl, st)
+              : launch_gemm_c<LAYER, __half>(p, grid, Cp, ctas, pdl, st);
 }
 
 template <int MODE, typename T16, int CP>
-cudaError_t launch_tail_t(const TailHeadParams& p, dim3 grid, cudaStream_t st) {
+cudaError_t launch_tail_t(const TailHeadParams& p, dim3 grid, bool pdl, cudaStream_t st) {
   auto kern = tailhead_kernel<MODE, T16, CP>;
   // same shared-memory carveout as the GEMM kernels, so the SMs are not reconfigured at every kernel boundary
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -764,17 +768,17 @@ cudaError_t launch_tail_t(const TailHeadParams& p, dim3 grid, cudaStream_t st) {
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 template <int MODE>
-cudaError_t launch_tail(const TailHeadParams& p, dim3 grid, bool bf16, int Cp, cudaStream_t st) {
+cudaError_t launch_tail(const TailHeadParams& p, dim3 grid, bool bf16, int Cp, bool pdl, cudaStream_t st) {
 #define LADINE_TAIL_CASE(CPV)                                                              \
   case CPV:                                                                                \
-    return bf16 ? launch_tail_t<MODE, __nv_bfloat16, CPV>(p, grid, st) : launch_tail_t<MODE, __half, CPV>(p, grid, st);
+    return bf16 ? launch_tail_t<MODE, __nv_bfloat16, CPV>(p, grid, pdl, st) : launch_tail_t<MODE, __half, CPV>(p, grid, pdl, st);
   switch (Cp) {
     LADINE_TAIL_CASE(2)
     LADINE_TAIL_CASE(4)
@@ -824,7 +828,6 @@ size_t tensor_gemm_smem_bytes(int Cp) {
 
 // 1 = cta_group::1 tiles of 128 rows, 2 = CTA pairs (cta_group::2) on 256-row tiles.  Pairs halve the
 // B-operand shared-memory/L2 traffic per SM but pad each member's rows to a multiple of 256.
-void set_use_pdl(bool on) { g_use_pdl = on; }
 
 // ------------------------------------------------------------------------------------------
 // static tile schedule
@@ -919,6 +922,7 @@ struct TensorChain {
   TailHeadParams tp{};
   dim3 tgrid;
   int grid = 0, K = 0, Fp = 0, Cp = 0, slot_base = 0, ctas = 1, ycur = 0;
+  bool pdl = false;
   float* ybuf[2] = {nullptr, nullptr};
   bool bf16 = false;
 
@@ -944,6 +948,7 @@ struct TensorChain {
     K = a.K;
     const int rows = a.N * a.D;
     ctas = choose_ctas(h, rows);
+    pdl = pdl_allowed(h, ctas);
     const int NBt = Fp / BN;
     if ((rows + BM - 1) / BM > 4096 || NBt > 1024) {
       *err = "too many rows per member for one launch group (max 524288 chains): tile the images (NestedEnsemble does)";
@@ -1021,7 +1026,7 @@ struct TensorChain {
     tp.y_prev = ybuf[ycur];
     tp.y_next = ybuf[ycur ^ 1];
     ycur ^= 1;
-    e = launch_tail<kInit>(tp, tgrid, bf16, Cp, st);
+    e = launch_tail<kInit>(tp, tgrid, bf16, Cp, pdl, st);
     if (e == cudaSuccess) ++*launches;
     return e;
   }
@@ -1037,12 +1042,12 @@ struct TensorChain {
     cudaError_t e;
     {
       ProfSpan ps(h, st, 0);
-      e = launch_gemm<2>(g2, grid, bf16, Cp, ctas, st);
+      e = launch_gemm<2>(g2, grid, bf16, Cp, ctas, pdl, st);
     }
     if (e != cudaSuccess) return e;
     {
       ProfSpan ps(h, st, 1);
-      e = launch_gemm<3>(g3, grid, bf16, Cp, ctas, st);
+      e = launch_gemm<3>(g3, grid, bf16, Cp, ctas, pdl, st);
     }
     if (e != cudaSuccess) return e;
     tp.coef = h_coef[t];
@@ -1057,10 +1062,10 @@ struct TensorChain {
     {
       ProfSpan ps(h, st, 2);
       if (last) {
-        e = launch_tail<kFinal>(tp, tgrid, bf16, Cp, st);
+        e = launch_tail<kFinal>(tp, tgrid, bf16, Cp, pdl, st);
       } else {
         set_head_rows(t - 1);
-        e = launch_tail<kMid>(tp, tgrid, bf16, Cp, st);
+        e = launch_tail<kMid>(tp, tgrid, bf16, Cp, pdl, st);
       }
     }
     if (e == cudaSuccess) *launches += 3;
@@ -1110,7 +1115,8 @@ cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int lay
   g.idesc = make_idesc(bf16, ctas);
   g.idesc_half = make_idesc(bf16, 1);
   const int grid = plan.units * ctas;
-  return layer == 2 ? launch_gemm<2>(g, grid, bf16, m->Cp, ctas, st) : launch_gemm<3>(g, grid, bf16, m->Cp, ctas, st);
+  return layer == 2 ? launch_gemm<2>(g, grid, bf16, m->Cp, ctas, false, st)
+                    : launch_gemm<3>(g, grid, bf16, m->Cp, ctas, false, st);
 }
 
 }  // namespace ladine

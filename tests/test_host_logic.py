@@ -249,3 +249,38 @@ def test_philox_noise_is_standard_normal_and_partition_invariant():
     assert np.array_equal(part, z[:, :, :, 25:40])
     member1 = pho.noise_tensor(1234, K=1, D=3, S=50, N=40, C=2, member_ids=[1])
     assert np.array_equal(member1[0], z[1])
+
+
+# ------------------------------------------------------------------ runner shim (host logic only)
+def test_runner_metrics_and_checkpoint_loader(tmp_path):
+    from nested_diffusion_b200.runner import (SampleCache, ensemble_metrics, load_noise_estimators,
+                                              temperature_for)
+
+    g = torch.Generator().manual_seed(3)
+    cache = SampleCache()
+    for _ in range(3):
+        cache.y0.append(torch.randn(40, 9, 2, generator=g) * 0.6 + torch.tensor([0.2, 0.7]))
+        cache.target.append(torch.randint(0, 2, (9,), generator=g))
+    m = ensemble_metrics(cache, 0.1737)
+    allv = torch.cat(cache.y0, dim=1)
+    tgt = torch.cat(cache.target)
+    mv = torch.cat([orc.majority_vote(s) for s in cache.y0])
+    assert torch.equal(m["majority_vote"], mv)
+    assert float(m["accuracy"]) == pytest.approx(float((mv == tgt).float().mean()))
+    prob = torch.cat([orc.ensemble_confidence(s, 0.1737) for s in cache.y0])
+    assert float(m["ece"]) == pytest.approx(float(orc.ece_l1(prob, tgt)), abs=1e-6)
+    for mine, ref in zip((m["var_correct"], m["var_incorrect"]), orc.class_variances(allv, mv, tgt)):
+        assert torch.allclose(mine, ref)
+    assert temperature_for("ISICSkinCancerAtkPGD") == 0.3162
+    with pytest.raises(NotImplementedError):
+        temperature_for("MNIST")
+    cfg = argparse.Namespace(diffusion=argparse.Namespace(timesteps=5, include_guidance=True),
+                             data=argparse.Namespace(num_classes=2, dataset="ChestXRay"),
+                             model=argparse.Namespace(data_dim=10, arch="linear", feature_dim=8, hidden_dim=6))
+    src = nd.ConditionalModel(cfg, guidance=True)
+    path = tmp_path / "diffu0_ckpt_best.pth"
+    torch.save({"noise_estimator": src.state_dict(), "optimizer": {}, "epoch": 7}, path)  # the reference's layout
+    (loaded,) = load_noise_estimators(cfg, [str(path)], "cpu")
+    assert not loaded.training
+    for k, v in src.state_dict().items():
+        assert torch.equal(v, loaded.state_dict()[k])
