@@ -130,9 +130,64 @@ def packed_member_of(model, precision: str = "auto") -> PackedMember:
     return pm
 
 
-def encode_features(model, x: torch.Tensor) -> torch.Tensor:
-    """``norm(encoder_x(x))`` in PyTorch (step-invariant; latent_model.py:170-171)."""
+# ------------------------------------------------------------------------------------------------
+# step-invariant encoder prologue (PyTorch library GEMMs)
+# ------------------------------------------------------------------------------------------------
+_SPLIT_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+SPLIT_TF32_MIN_IN_FEATURES = 16384  # only the image-sized first layer (150528 -> 4096) is worth splitting
+
+
+def _tf32_hi(t: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest onto the TF32 grid (10 explicit mantissa bits), kept in FP32 storage."""
+    bits = t.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def split_tf32_linear(x: torch.Tensor, lin: torch.nn.Linear) -> torch.Tensor:
+    """``lin(x)`` through three TF32 tensor-core GEMMs: W = W_hi + W_lo, x = x_hi + x_lo with every part exactly
+    TF32-representable, x W^T ~= x_hi W_hi^T + x_hi W_lo^T + x_lo W_hi^T.  OPT-IN (``mode="tf32x3"``): measured on
+    B200 it is 2.3x faster than the FP32 GEMM (3.9 -> 1.7 ms for [70,150528]x[150528,4096]) and ~5x more accurate than
+    plain TF32, but NOT FP32-grade -- 6e-5 relative at K=20000 against FP32's 7e-7, because the tensor core's
+    accumulator is not an IEEE FP32 adder.  The parity-tested default therefore stays the plain FP32 GEMM.
+    The split of W is cached per module and refreshed when the weight changes."""
+    w = lin.weight
+    key = (w.data_ptr(), w._version, str(w.device))
+    hit = _SPLIT_CACHE.get(lin)
+    if hit is None or hit[0] != key:
+        w32 = w.detach().to(torch.float32)
+        w_hi = _tf32_hi(w32)
+        w_lo = _tf32_hi(w32 - w_hi)
+        hit = (key, w_hi, w_lo)
+        _SPLIT_CACHE[lin] = hit
+    _, w_hi, w_lo = hit
+    x32 = x.to(torch.float32)
+    x_hi = _tf32_hi(x32)
+    x_lo = _tf32_hi(x32 - x_hi)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        out = x_hi @ w_lo.t()
+        out += x_lo @ w_hi.t()
+        out += x_hi @ w_hi.t()       # largest term last
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return out if lin.bias is None else out + lin.bias
+
+
+def encode_features(model, x: torch.Tensor, mode: str = "fp32") -> torch.Tensor:
+    """``norm(encoder_x(x))`` in PyTorch (step-invariant; latent_model.py:170-171).
+
+    mode "fp32" (default): the module as is.  "tf32x3": on CUDA, an MLP encoder whose first Linear reads >= 16384
+    features runs that layer through ``split_tf32_linear`` (faster, ~6e-5 relative -- see there)."""
     with torch.no_grad():
+        enc = getattr(model, "encoder_x", None)
+        first = enc[0] if isinstance(enc, torch.nn.Sequential) and len(enc) > 0 else None
+        if (mode == "tf32x3" and x.is_cuda and isinstance(first, torch.nn.Linear)
+                and first.in_features >= SPLIT_TF32_MIN_IN_FEATURES and not model.training):
+            h = split_tf32_linear(x, first)
+            for layer in list(enc)[1:]:
+                h = layer(h)
+            return model.norm(h)
         if hasattr(model, "encode"):
             return model.encode(x)
         return model.norm(model.encoder_x(x))

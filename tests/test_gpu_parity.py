@@ -410,3 +410,54 @@ def test_runner_shim_matches_restated_reference_loop():
     want_piw = orc.mean_piw_per_class(torch.cat(y_all, dim=1), mv, tgt)
     for got, want in zip((tester.last_metrics["piw_correct"], tester.last_metrics["piw_incorrect"]), want_piw):
         assert torch.allclose(got, want, atol=1e-4, equal_nan=True)
+
+
+def test_split_tf32_encoder_option_accuracy():
+    """The opt-in 3xTF32 split of the image-sized encoder layer: better than plain TF32, not FP32-grade (which is
+    why FP32 stays the default)."""
+    from nested_diffusion_b200 import engine
+
+    g = torch.Generator().manual_seed(2)
+    lin = torch.nn.Linear(20000, 512).cuda()
+    x = torch.rand(70, 20000, generator=g).cuda()
+    with torch.no_grad():
+        ref64 = (x.double() @ lin.weight.double().t() + lin.bias.double())
+        fp32 = torch.nn.functional.linear(x, lin.weight, lin.bias)
+        split = engine.split_tf32_linear(x, lin)
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        tf32 = torch.nn.functional.linear(x, lin.weight, lin.bias)
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    scale = float(ref64.abs().max())
+    e_split = float((split.double() - ref64).abs().max()) / scale
+    e_fp32 = float((fp32.double() - ref64).abs().max()) / scale
+    e_tf32 = float((tf32.double() - ref64).abs().max()) / scale
+    print(f"rel err vs FP64: split {e_split:.2e}, fp32 {e_fp32:.2e}, plain tf32 {e_tf32:.2e}")
+    assert e_fp32 <= 5e-6 and e_split <= 2e-4 and e_tf32 > 3 * e_split
+
+
+@pytest.mark.slow
+def test_full_shipped_shape_explicit_steps():
+    """The whole shipped ConditionalModel (Dx=150528, H=F=4096, 2.59 GiB) through the drop-in p_sample /
+    p_sample_t_1to0 vs the reference's recorded outputs: covers the 3xTF32 encoder prologue + the tensor path."""
+    from nested_diffusion_b200 import diffusion_utils as du
+
+    fx = Fixture("shipped_dims_steps")
+    m = fx.meta
+    sd = orc.synth_state_dict(m["sd_seed"], m["F"], m["H"], m["Dx"], m["C"], m["T"])
+    x, yhat = orc.synth_inputs(m["in_seed"], m["B"], m["Dx"], m["C"])
+    alphas, omabs = fx.schedule()
+    model = make_model(dict(m, guidance=True), sd)
+    del sd
+    xg, yg, y_in = x.cuda(), yhat.cuda(), fx["y_in"].cuda()
+    with torch.no_grad():
+        from nested_diffusion_b200 import engine
+        xf = engine.encode_features(model, xg)
+        assert rel_err(xf[:, :64].cpu(), fx["xf_sample"]) <= 2e-5
+        for prec in ("fp16", "bf16"):
+            for i, t in enumerate(m["steps"]):
+                out = du.p_sample(model, xg, y_in, yg, yg, t, alphas.cuda(), omabs.cuda(), noise=fx["z"][i].cuda(),
+                                  precision=prec).cpu()
+                assert rel_err(out, fx["y_out"][i]) <= TOL[prec], (prec, t)
+            last = du.p_sample_t_1to0(model, xg, y_in, yg, yg, omabs.cuda(), precision=prec).cpu()
+            assert rel_err(last, fx["y_final"]) <= TOL[prec]
