@@ -461,3 +461,42 @@ def test_full_shipped_shape_explicit_steps():
                 assert rel_err(out, fx["y_out"][i]) <= TOL[prec], (prec, t)
             last = du.p_sample_t_1to0(model, xg, y_in, yg, yg, omabs.cuda(), precision=prec).cpu()
             assert rel_err(last, fx["y_final"]) <= TOL[prec]
+
+
+@pytest.mark.parametrize("F,C,guidance,K,N,D,T,prec", [
+    (300, 3, True, 2, 9, 2, 7, "fp16"),      # F padded 300 -> 512, Cp = 4
+    (256, 10, False, 1, 5, 3, 6, "fp16"),    # 10 classes (Cp = 16), no guidance
+    (256, 2, True, 9, 4, 2, 5, "bf16"),      # K = 9 > LADINE_MAX_GROUP: two launch groups
+    (256, 2, True, 2, 3, 40, 5, "fp16"),     # D = 40 > 32 draws per tail/head CTA
+    (256, 2, True, 1, 1, 1, 1, "fp16"),      # a single chain, a single step
+    (100, 2, True, 2, 33, 2, 9, "fp32"),     # resident path, F padded 100 -> 128, ragged row tile
+    (32, 5, False, 3, 40, 1, 4, "fp32"),     # smallest resident geometry, 5 classes, no guidance
+])
+def test_shape_matrix_vs_oracle(F, C, guidance, K, N, D, T, prec):
+    """Edge shapes through ladine_sample vs the oracle's packed form (same operand rounding on the tensor path)."""
+    import nested_diffusion_b200 as nd
+    from nested_diffusion_b200 import engine
+    from nested_diffusion_b200.schedule import coef_table
+
+    sds = [orc.synth_state_dict(1200 + k, F, 8, 12, C, T, guidance=guidance) for k in range(K)]
+    pms = [nd.PackedMember({k: v.cuda() for k, v in sd.items()}, n_steps=T, precision=prec) for sd in sds]
+    g = torch.Generator().manual_seed(21)
+    xf = torch.randn(K, N, F, generator=g)
+    yh = torch.softmax(torch.randn(K, N, C, generator=g), -1)
+    n_slots = T  # 1 (y_T) + T - 1 noisy steps
+    noise = torch.randn(K, D, n_slots, N, C, generator=g)
+    alphas, omabs = orc.schedule_tensors(orc.make_beta_schedule("linear", max(T, 2), 1e-4, 0.02))
+    alphas, omabs = alphas[:T], omabs[:T]
+    coef = coef_table(alphas, omabs, T)
+    got = engine.sample_chains(pms, xf.cuda(), yh.cuda(), yh.cuda(), coef, D, noise=noise.cuda(), trajectory=True,
+                               temperature=0.3)
+    odt = ODT.get(prec)
+    with torch.no_grad():
+        want = torch.stack([torch.stack([torch.stack(
+            orc.packed_sample(sds[k], xf[k], yh[k], yh[k], T, alphas, omabs, noise[k, d], operand_dtype=odt,
+                              trajectory=True)) for d in range(D)]) for k in range(K)])   # [K, D, T+1, N, C]
+    tol = 1e-5 if prec == "fp32" else (2e-4 if prec == "bf16" else 2e-5)
+    assert got["traj"].shape == want.shape
+    assert rel_err(got["traj"].cpu(), want) <= tol
+    assert torch.equal(got["traj"][:, :, -1], got["y"])
+    assert torch.allclose(got["probs"].cpu(), orc.convert_to_prob(got["y"].cpu(), 0.3), atol=2e-6)
