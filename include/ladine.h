@@ -149,7 +149,9 @@ uint64_t ladine_workspace_bytes(const ladine_handle* h);
  *   "ctas" (0 auto | 1 | 2): GEMM tile geometry -- single CTAs (cta_group::1, 128x256 tiles) or CTA pairs
  *       (cta_group::2, 256x256 tiles + 2x64-row half tiles); auto picks pairs when the rows pad well;
  *   "pair_gain_permille": measured per-tile speed ratio pair/single used by the auto choice (default 1080);
- *   "pdl" (0 default | 1): programmatic dependent launch, applied to single-CTA chains only. */
+ *   "pdl" (0 default | 1): programmatic dependent launch, applied to single-CTA chains only;
+ *   "fuse" (0 default | 1): run the tail + head of each reverse step inside the layer-3 GEMM kernel (helper warps
+ *       gated by per-row-group arrival counters) instead of a separate kernel; bitwise identical results. */
 int ladine_set_option(ladine_handle* h, const char* key, int64_t value);
 
 /* Optional per-kernel timing of the tensor-core path.  When enabled, ladine_sample brackets every

@@ -463,12 +463,13 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
   const uint64_t lane_base = off;
   uint64_t lo = 0;
   const uint64_t o_u = lo; lo = align_up(lo + (uint64_t)gmax * a->N * Fp * 4, 1024);
-  uint64_t o_h1 = 0, o_h2 = 0, o_part = 0, o_y = 0, o_sched = 0;
+  uint64_t o_h1 = 0, o_h2 = 0, o_part = 0, o_y = 0, o_sched = 0, o_arr = 0;
   if (tensor) {
     o_h1 = lo; lo = align_up(lo + m_total * Fp * 2, 1024);
     o_h2 = lo; lo = align_up(lo + m_total * Fp * 2, 1024);
     o_part = lo; lo = align_up(lo + m_total * (Fp / 256) * 2 * Cp * 4, 1024);
     o_sched = lo; lo = align_up(lo + sched_bytes_bound(gmax, rows, Fp / 256), 1024);
+    o_arr = lo; lo = align_up(lo + (uint64_t)gmax * ((rows + 127) / 128 + 1) * 2 * sizeof(int), 1024);
     o_y = lo; lo = align_up(lo + 2 * m_total * Cp * 4, 1024);
   }
   const uint64_t lane_bytes = lo;
@@ -536,9 +537,10 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
         tw.ybuf = reinterpret_cast<float*>(lw + o_y);
         tw.u = d_u;
         tw.sched = reinterpret_cast<int32_t*>(lw + o_sched);
+        tw.arrivals = reinterpret_cast<int*>(lw + o_arr);
         std::string err;
         chains[l] = tensor_chain_create(h, members + k0, g, ids, h_coef, tw, si.n_slots, si.n_traj, ls,
-                                        &h->last_launches, &err, &e);
+                                        /*single_lane=*/nl == 1, &h->last_launches, &err, &e);
         if (!chains[l]) status = err.empty() ? fail_cuda(h, e, "tensor-core sampler launch") : fail(h, LADINE_ERR_CUDA, err);
       }
     }
@@ -567,6 +569,10 @@ int ladine_set_option(ladine_handle* h, const char* key, int64_t value) {
   if (strcmp(key, "lanes") == 0) {
     if (value < 1 || value > ladine_handle::kMaxLanes) return fail(h, LADINE_ERR_INVALID, "lanes must be in [1, 4]");
     h->lanes = (int)value;
+    return LADINE_OK;
+  }
+  if (strcmp(key, "fuse") == 0) {
+    h->fuse = value != 0;
     return LADINE_OK;
   }
   if (strcmp(key, "pdl") == 0) {

@@ -48,6 +48,10 @@ struct ladine_handle {
   // lanes: independent member groups run concurrently on internal streams (tensor path)
   static constexpr int kMaxLanes = 4;
   int lanes = 1;
+  // fold the tail + head of each step into the layer-3 GEMM kernel (helper warps; single-lane chains, <= 8 classes).
+  // Bitwise identical to the separate tail/head kernel; measured 1-3 % SLOWER at config 2 (the helpers compete with
+  // the SMEM-port-bound mainloop and the last row groups drain after the last MMA), so it is opt-in.
+  bool fuse = false;
   bool pdl = false;         // programmatic dependent launch: opt-in, single-CTA chains only (see ladine_tensor.cu)
   int ctas = 0;             // 0 = choose per call, 1 = cta_group::1, 2 = cta_group::2 CTA pairs
   double pair_gain = 1.08;   // measured throughput ratio pair/single per useful tile (see choose_ctas)
@@ -83,12 +87,14 @@ struct TensorWorkspace {
   float* part;   // [K * rows_pad, Fp / 256, 2, Cp]  (one lin4 partial per 128-column slot)
   float* ybuf;   // 2 x [K * rows_pad, Cp] (ping-pong chain state)
   float* u;      // [K, N, Fp]
-  int32_t* sched;  // static tile schedule of this lane's GEMM launches
+  int32_t* sched;  // static tile schedules of this lane's GEMM launches (layer 2 | layer 3)
+  int* arrivals;   // row-group arrival counters of the fused tail + head
 };
 struct TensorChain;  // one lane: a group of members advancing through the reverse steps on one stream
 TensorChain* tensor_chain_create(ladine_handle* h, const ladine_member* const* members, const ladine_sample_args& a,
                                  const ChainIds& ids, const StepCoef* h_coef, const TensorWorkspace& ws, int n_slots,
-                                 int n_traj, cudaStream_t st, int64_t* launches, std::string* err, cudaError_t* status);
+                                 int n_traj, cudaStream_t st, bool single_lane, int64_t* launches, std::string* err,
+                                 cudaError_t* status);
 cudaError_t tensor_chain_step(TensorChain* c, int t, int64_t* launches);
 void tensor_chain_destroy(TensorChain* c);
 cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int layer, int t, const void* h_in, int rows,

@@ -11,9 +11,11 @@
 // where A_l/C_l fold gamma_l[t], the Linear bias and the eval-mode BatchNorm.
 //
 // GEMM kernel: persistent, warp-specialised, one CTA per SM.
-//   warp 0      TMA producer   (cp.async.bulk.tensor 2D, 128B swizzle, 4-stage mbarrier ring)
-//   warp 1      MMA issuer     (tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16, one thread)
-//   warps 2..5  epilogue       (tcgen05.ld 32x32b, scale/shift + softplus in the log2 domain, store)
+//   warps 0..3  epilogue       (tcgen05.ld 32x32b, scale/shift + softplus in the log2 domain, store; layer 3: fused
+//                               lin4 partials and, once a row group is complete, the tail + head of the step)
+//   warps 4..7  helpers        (layer 3: tail + head of the reverse step for row groups whose column tiles are all in)
+//   warp 8      TMA producer   (cp.async.bulk.tensor 2D, 128B swizzle, mbarrier ring)
+//   warp 9      MMA issuer     (tcgen05.mma kind::f16, cta_group::1 M=128 / cta_group::2 M=256, N=256 K=16, one thread)
 //   TMEM: 2 accumulator stages x 256 columns so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cstdio>
 
@@ -28,8 +30,15 @@ constexpr int BK = 64;    // K per stage    (64 x 2 B = one 128-byte swizzle row
 constexpr int UK = 16;    // K per tcgen05.mma (kind::f16)
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * BN;  // 512
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;
 constexpr int kEpiThreads = 128;
+// Warp roles.  The single-thread TMA producer and MMA issuer get the HIGHEST warp ids: each shares an SM sub-partition
+// scheduler with one epilogue warp, and the arbiter favours the higher warp id, so a busy epilogue (fused tail + head)
+// can never delay the instructions that keep the tensor pipe fed.
+constexpr int kEpiWarps = kEpiThreads / 32;   // warps 0..3: epilogue (TMEM lane quadrant = warp id)
+constexpr int kHelperWarp0 = 4;               // warps 4..7: fused tail + head jobs (layer 3), idle otherwise
+constexpr int kProducerWarp = 8;
+constexpr int kMmaWarp = 9;
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -131,6 +140,35 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 // ------------------------------------------------------------------------------------------
 // GEMM + fused epilogue
 // ------------------------------------------------------------------------------------------
+enum TailMode { kInit = 0, kMid = 1, kFinal = 2 };
+
+struct TailHeadParams {
+  const float* A1[LADINE_MAX_GROUP];   // row of the NEXT step (t-1), x log2e
+  const float* C1[LADINE_MAX_GROUP];
+  const float* W1y[LADINE_MAX_GROUP];  // [Fp, Cp]
+  const float* b4[LADINE_MAX_GROUP];
+  const float* part;   // [M_total, NB, Cp]
+  const float* y_prev; // [M_total, Cp]  chain state before this step (ping-pong: column-split CTAs all read it)
+  float* y_next;       // [M_total, Cp]  chain state after this step (written by column split 0)
+  const float* xf;     // [K, N, Fin]
+  const float* u;      // [K, N, Fp]
+  const float* ytmean; // [K, N, C]
+  const float* y_init; // [K, D, N, C] or null (kInit only)
+  const float* noise;  // [K, D, S, N, C] or null
+  void* h1;            // [M_total, Fp] 16-bit
+  float* y_out;        // kFinal / last step
+  float* traj_out;
+  float* prob_out;
+  float temperature;
+  StepCoef coef;       // coefficients of the step being finished (unused for kInit)
+  uint64_t seed;
+  ChainIds ids;
+  int t;               // table index of the step being finished (kInit: unused)
+  int slot;            // noise slot / trajectory entry consumed-written by this launch
+  int traj_entry;
+  int N, D, C, Fin, Fp, NB, rows_pad, n_slots, n_traj, dchunk, write_out, colsplit;
+};
+
 struct GemmParams {
   CUtensorMap tmA;                     // activations in  [M_total, Fp] 16-bit, box 64 x 128
   CUtensorMap tmB[LADINE_MAX_GROUP];   // member weights  [Fp, Fp]      16-bit, box 64 x (256 / CTAS)
@@ -148,6 +186,16 @@ struct GemmParams {
   int sched_stride;
   uint32_t idesc;                      // full tiles: M = 128 * CTAS
   uint32_t idesc_half;                 // pair half tiles: M = 128 (64 rows per CTA)
+  // ---- layer 3 with the tail + head fused in (fuse != 0) ----
+  // After a CTA has written its lin4 partials it signals the row group's arrival counter; when all NB column
+  // tiles of the group are in, every one of those CTAs finishes the reverse step for its rows (eps, posterior
+  // update -- recomputed identically by each) and produces h1 of the next step for ITS 256 columns.
+  int fuse;
+  int do_head;                         // 0 on the last step of the chain (no next h1)
+  int mblk_total;                      // row tiles per member (full + half)
+  int* group_arrivals;                 // [K * mblk_total * CTAS], monotonically increasing over the chain
+  int arrivals_target;                 // NB * (layer-3 launches of this chain so far, this one included)
+  TailHeadParams th;
 };
 
 struct TileCode {
@@ -176,7 +224,7 @@ struct __align__(8) GemmBarriers {
   uint64_t acc_full[kAccStages];
   uint64_t acc_empty[kAccStages];
   uint32_t tmem_base;
-  uint32_t pad;
+  int published;   // layer 3, fused: tiles of this CTA whose lin4 partials are out (epilogue -> helper warps)
 };
 
 // 256-bit global store (one full 32-byte sector per thread)
@@ -247,6 +295,142 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
+// Finish reverse step th.t for the CTA's rows [row_base, row_base + nrows) of member k and (unless it is the last
+// step) write their h1 of the next step for the 256 columns of N tile nb.  Called by the 128 epilogue threads.
+//   tail : thread e < nrows owns row row_base + e: eps = b4 + sum of the 2 * NB column-slot partials, posterior
+//          update (reference op order), y -> sYn (and, from the nb == 0 CTA, to y_next / trajectory / outputs);
+//   head : thread e owns columns 2e, 2e+1 of the tile and walks the rows; per-column constants live in registers
+//          and the per-image ones (u, xf) are refreshed when the image changes, so the shared-memory/L1 port -- the
+//          resource the GEMM mainloop is bound by -- sees one broadcast LDS and one coalesced 128-byte store per row.
+// Same arithmetic, in the same order, as tailhead_kernel: fused and unfused chains are bitwise identical.
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+
+template <typename T16, int CP>
+__device__ __forceinline__ void fused_tail_head(const TailHeadParams& th, float* __restrict__ sYn_generic, int k, int nb, int NB,
+                                                int row_base, int nrows, int rows_valid, size_t grow_base, int e,
+                                                bool publish, bool do_head) {
+  const int C = th.C;
+  const uint32_t sYn = smem_u32(sYn_generic);   // explicit shared-window accesses (a generic LD costs ~3x an LDS)
+  if (e < nrows && row_base + e < rows_valid) {
+    const int row_m = row_base + e;
+    const size_t grow = grow_base + e;
+    const int n = row_m / th.D, d = row_m - n * th.D;
+    // The row's partials are 2 * NB * CP contiguous floats written by other SMs: independent 128-bit loads through
+    // L2 first (a dependent load-add chain would cost one L2 round trip per slot), then slot-ascending adds.
+    float eps[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) eps[c] = c < C ? __ldg(th.b4[k] + c) : 0.f;
+    {
+      const float4* pp4 = reinterpret_cast<const float4*>(th.part + (grow * NB) * 2 * CP);
+      const int n4 = 2 * NB * CP / 4;
+      for (int i0 = 0; i0 < n4; i0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (i0 + j) < n4 ? __ldcg(pp4 + i0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if ((i0 + j) < n4) {
+            const float e4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int c = (4 * j + q) % CP;   // == (4 * (i0 + j) + q) % CP: i0 is a multiple of 8, CP divides 32
+#pragma unroll
+              for (int cc = 0; cc < CP; ++cc)
+                if (cc == c) eps[cc] += e4[q];
+            }
+          }
+        }
+      }
+    }
+    float yn[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) yn[c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+      if (c < C) {
+        const float mu = __ldg(th.ytmean + ((size_t)k * th.N + n) * C + c);
+        const float y = th.y_prev[grow * CP + c];
+        float v;
+        if (th.t > 0) {
+          const float z = th.noise
+                              ? __ldg(th.noise + ((((size_t)k * th.D + d) * th.n_slots + th.slot) * th.N + n) * C + c)
+                              : philox_normal(th.seed, th.ids.chain(k, d, n), (uint32_t)th.slot, c);
+          v = posterior_step_op(th.coef, y, mu, eps[c], z);
+        } else {
+          v = y0_reparam_op(th.coef, y, mu, eps[c]);
+        }
+        yn[c] = v;
+        if (publish) {
+          th.y_next[grow * CP + c] = v;
+          if (th.traj_out && th.traj_entry >= 0)
+            th.traj_out[((((size_t)k * th.D + d) * th.n_traj + th.traj_entry) * th.N + n) * C + c] = v;
+          if (th.write_out) th.y_out[(((size_t)k * th.D + d) * th.N + n) * C + c] = v;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CP; ++c) sts_f32(sYn + (uint32_t)(e * CP + c) * 4u, yn[c]);
+    if (publish && th.write_out && th.prob_out) {
+      float mx = -INFINITY;
+      for (int c = 0; c < C; ++c) mx = fmaxf(mx, -(yn[c] - 1.0f) * (yn[c] - 1.0f) / th.temperature);
+      float sum = 0.f;
+      for (int c = 0; c < C; ++c) sum += expf(-(yn[c] - 1.0f) * (yn[c] - 1.0f) / th.temperature - mx);
+      const size_t o = (((size_t)k * th.D + d) * th.N + n) * C;
+      for (int c = 0; c < C; ++c)
+        th.prob_out[o + c] = expf(-(yn[c] - 1.0f) * (yn[c] - 1.0f) / th.temperature - mx) / sum;
+    }
+  }
+  if (!do_head) return;
+  asm volatile("bar.sync 2, 128;" ::: "memory");   // sYn complete (barrier 2 = the 128 helper threads)
+
+  const int gcol = nb * BN + 2 * e;   // this thread's two features
+  float a1[2], c1[2], pc[2][CP];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    a1[j] = __ldg(th.A1[k] + gcol + j);
+    c1[j] = __ldg(th.C1[k] + gcol + j);
+#pragma unroll
+    for (int c = 0; c < CP; ++c) pc[j][c] = a1[j] * __ldg(th.W1y[k] + (size_t)(gcol + j) * CP + c);
+  }
+  const int last = min(nrows, rows_valid - row_base);   // rows of this CTA that exist
+  int n = row_base / th.D, d = row_base - n * th.D;
+  float q[2] = {0.f, 0.f}, xl[2] = {0.f, 0.f};
+  bool fresh = true;
+  uint32_t* hcol = reinterpret_cast<uint32_t*>(reinterpret_cast<T16*>(th.h1) + grow_base * th.Fp + gcol);
+  const size_t hstride = (size_t)th.Fp / 2;   // uint32 (two 16-bit values) per row
+#pragma unroll 4
+  for (int r = 0; r < last; ++r) {
+    if (fresh) {
+      const float* urow = th.u + ((size_t)k * th.N + n) * th.Fp + gcol;
+      const float* xfrow = th.xf + ((size_t)k * th.N + n) * th.Fin + gcol;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        q[j] = fmaf(a1[j], __ldg(urow + j), c1[j]);
+        xl[j] = ((gcol + j) < th.Fin ? __ldg(xfrow + j) : 0.f) * kLn2;
+      }
+      fresh = false;
+    }
+    float hv[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float v2 = q[j];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) v2 = fmaf(pc[j][c], lds_f32(sYn + (uint32_t)(r * CP + c) * 4u), v2);
+      const float t = v2 > kSoftplusThreshold * kLog2e ? v2 : lg2_approx(1.0f + ex2_approx(v2));
+      hv[j] = t * xl[j];
+    }
+    hcol[(size_t)r * hstride] = Pack16<T16>::pack(hv[0], hv[1]);   // a warp writes 128 contiguous bytes of the row
+    if (++d == th.D) { d = 0; ++n; fresh = true; }
+  }
+}
+
 template <int LAYER, typename T16, int CP, int CTAS>
 __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<CTAS>;
@@ -257,7 +441,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
   uint8_t* sA = smem;                                    // kStages x 16 KiB
   uint8_t* sB = smem + kStages * Cfg::kABytes;           // kStages x 32 (16) KiB
   float* sEpi = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);  // scale[256] shift[256] (W4[CP][256])
-  GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(sEpi + (LAYER == 3 ? BN * (2 + CP) : 2 * BN));
+  // layer 3: scale[256] | shift[256] | W4[CP][256] | y_next of this CTA's rows [128][CP] (fused tail + head)
+  constexpr int kEpiFloats = LAYER == 3 ? BN * (2 + CP) + BM * CP : 2 * BN;
+  GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(sEpi + kEpiFloats);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;   // position in the CTA pair; 0 issues the MMAs
@@ -275,10 +461,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
       mbar_init(smem_u32(&bars->acc_full[s]), 1);
       mbar_init(smem_u32(&bars->acc_empty[s]), CTAS * (kEpiThreads / 32));
     }
+    bars->published = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&p.tmA);
   }
-  if (warp == 2) {
+  if (warp == 0) {
     if (CTAS == 2) tmem_alloc_pair(smem_u32(&bars->tmem_base), kTmemCols);
     else tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
   }
@@ -291,7 +478,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
 
   const int32_t* my_sched = p.sched + (size_t)unit * p.sched_stride;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ===================== TMA producer (one per CTA) =====================
     if (lane == 0) {
       int stage = 0;
@@ -321,7 +508,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (single thread; leader CTA of a pair) =====================
     if (lane == 0 && rank == 0) {
       int stage = 0;
@@ -358,10 +545,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
         else umma_commit(smem_u32(&bars->acc_full[as]));
       }
     }
-  } else {
-    // ===================== epilogue (warps 2..5), this CTA's rows x 256 columns =====================
-    const int et = threadIdx.x - 64;         // 0..127
-    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+  } else if (warp < kEpiWarps) {
+    // ===================== epilogue (warps 0..3), this CTA's rows x 256 columns =====================
+    const int et = threadIdx.x;              // 0..127
+    const int quad = warp;                   // TMEM lane quadrant this warp may access
     float* sScale = sEpi;
     float* sShift = sEpi + BN;
     float* sW4 = sEpi + 2 * BN;              // [CP][BN]
@@ -480,12 +667,69 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
         if (CTAS == 2) mbar_arrive_cluster(mapa_rank(eb, 0));
         else mbar_arrive(eb);
       }
+      if (LAYER == 3 && CP <= 8) {
+        if (p.fuse) {
+          // publish: my partials are visible GPU-wide (fence) for all 128 rows (barrier) before the row group is
+          // signalled; then tell this CTA's helper warps that job `it` exists
+          __threadfence();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            int* ctr = p.group_arrivals + ((size_t)member * p.mblk_total + tc.mb) * CTAS + rank;
+            asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ctr) : "memory");
+            asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(&bars->published)), "r"(it + 1) : "memory");
+          }
+        }
+      }
+    }
+  } else if (warp < kHelperWarp0 + 4) {
+    // ===================== helpers (warps 4..7): fused tail + head, decoupled from the accumulator pipeline ==========
+    // Job j = scheduled tile j of this CTA.  It can run once (a) this CTA's epilogue has published tile j and (b) all
+    // NB column tiles of the row group have arrived.  Arrivals never wait for a helper, so the blocking waits below
+    // cannot dead-lock, whatever the order in which CTAs become resident.
+    if (LAYER == 3 && CP <= 8) {
+      if (p.fuse) {
+        const int ht = threadIdx.x - kHelperWarp0 * 32;   // 0..127
+        float* sYn = sEpi + BN * (2 + CP);
+        for (int job = 0;; ++job) {
+          const int32_t code = __ldg(my_sched + job);
+          if (code < 0) break;
+          if (ht == 0) {
+            const TileCode tc(code);
+            const int* ctr = p.group_arrivals + ((size_t)tc.member * p.mblk_total + tc.mb) * CTAS + rank;
+            const long long t0 = clock64();
+            int pub = 0, seen = 0;
+            // relaxed polls with back-off (an acquire load at GPU scope invalidates the SM's L1 on every poll and the
+            // spinning thread would steal issue slots from the epilogue); one acquire fence once the data is there
+            for (;;) {
+              asm volatile("ld.relaxed.cta.shared.s32 %0, [%1];" : "=r"(pub) : "r"(smem_u32(&bars->published)) : "memory");
+              if (pub > job) {
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+                if (seen >= p.arrivals_target) break;
+              }
+              if (clock64() - t0 > 8000000000LL) {
+                printf("ladine: helper wait timeout block=%d job=%d published=%d seen=%d target=%d\n", (int)blockIdx.x, job,
+                       pub, seen, p.arrivals_target);
+                __trap();
+              }
+              __nanosleep(500);
+            }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          const TileCode tc(code);
+          const bool half = CTAS == 2 && tc.half;
+          const int row_base = tc.mb * (BM * CTAS) + (int)rank * (half ? BM / 2 : BM);
+          fused_tail_head<T16, CP>(p.th, sYn, tc.member, tc.nb, p.NB, row_base, half ? BM / 2 : BM, p.rows,
+                                   (size_t)tc.member * p.rows_pad + row_base, ht, /*publish=*/tc.nb == 0, p.do_head != 0);
+          asm volatile("bar.sync 2, 128;" ::: "memory");   // sYn is rewritten by the next job
+        }
+      }
     }
   }
 
   tc_fence_before();
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();   // pair: the peer's smem/TMEM stay live until both are done
-  if (warp == 2) {
+  if (warp == 0) {
     tc_fence_after();
     if (CTAS == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
     else tmem_dealloc(tmem_base, kTmemCols);
@@ -495,35 +739,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
 // ------------------------------------------------------------------------------------------
 // tail (posterior update of step t) + head (lin1 of step t-1)
 // ------------------------------------------------------------------------------------------
-enum TailMode { kInit = 0, kMid = 1, kFinal = 2 };
-
-struct TailHeadParams {
-  const float* A1[LADINE_MAX_GROUP];   // row of the NEXT step (t-1), x log2e
-  const float* C1[LADINE_MAX_GROUP];
-  const float* W1y[LADINE_MAX_GROUP];  // [Fp, Cp]
-  const float* b4[LADINE_MAX_GROUP];
-  const float* part;   // [M_total, NB, Cp]
-  const float* y_prev; // [M_total, Cp]  chain state before this step (ping-pong: column-split CTAs all read it)
-  float* y_next;       // [M_total, Cp]  chain state after this step (written by column split 0)
-  const float* xf;     // [K, N, Fin]
-  const float* u;      // [K, N, Fp]
-  const float* ytmean; // [K, N, C]
-  const float* y_init; // [K, D, N, C] or null (kInit only)
-  const float* noise;  // [K, D, S, N, C] or null
-  void* h1;            // [M_total, Fp] 16-bit
-  float* y_out;        // kFinal / last step
-  float* traj_out;
-  float* prob_out;
-  float temperature;
-  StepCoef coef;       // coefficients of the step being finished (unused for kInit)
-  uint64_t seed;
-  ChainIds ids;
-  int t;               // table index of the step being finished (kInit: unused)
-  int slot;            // noise slot / trajectory entry consumed-written by this launch
-  int traj_entry;
-  int N, D, C, Fin, Fp, NB, rows_pad, n_slots, n_traj, dchunk, write_out, colsplit;
-};
-
 constexpr int kTailThreads = 128;
 constexpr int kTailCols = kTailThreads * 8;  // features per CTA: 8 per thread
 constexpr int kTailMaxRows = 32;  // draws handled per CTA
@@ -543,6 +758,9 @@ __global__ void __launch_bounds__(kTailThreads) tailhead_kernel(const __grid_con
   pdl_wait();
 
   // ---------------- tail: finish step t for rows (k, n, d0..d0+nd) ----------------
+  if (CP != C)
+    for (int i = tid; i < nd * CP; i += kTailThreads) sY[i] = 0.f;   // padded classes read as 0 by the head
+  if (CP != C) __syncthreads();
   for (int i = tid; i < nd * C; i += kTailThreads) {
     const int dl = i / C, c = i - dl * C;
     const int d = d0 + dl;
@@ -607,8 +825,11 @@ __global__ void __launch_bounds__(kTailThreads) tailhead_kernel(const __grid_con
   const float* xfrow = p.xf + ((size_t)k * p.N + n) * p.Fin;
   const float* urow = p.u + ((size_t)k * p.N + n) * p.Fp;
   for (int f0 = cs * kTailCols + tid * 8; f0 < p.Fp; f0 += p.colsplit * kTailCols) {
-    float a1[8], c1[8], uu[8], xx[8], w1[8][CP];
+    // per-column constants of this step, folded once per CTA:  v2 = sum_c pc[c] * y[c] + q  (log2 domain),
+    // h1 = softplus(v2 / log2e) * xf = t * xl  with  t = lg2(1 + 2^v2) (or v2 itself when large), xl = xf * ln2
+    float q[8], xl[8], pc[8][CP];
     {
+      float a1[8], c1[8], uu[8];
       const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.A1[k] + f0));
       const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.A1[k] + f0 + 4));
       a1[0] = t0.x; a1[1] = t0.y; a1[2] = t0.z; a1[3] = t0.w; a1[4] = t1.x; a1[5] = t1.y; a1[6] = t1.z; a1[7] = t1.w;
@@ -620,30 +841,32 @@ __global__ void __launch_bounds__(kTailThreads) tailhead_kernel(const __grid_con
       uu[0] = u0.x; uu[1] = u0.y; uu[2] = u0.z; uu[3] = u0.w; uu[4] = u1.x; uu[5] = u1.y; uu[6] = u1.z; uu[7] = u1.w;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        xx[j] = (f0 + j) < p.Fin ? __ldg(xfrow + f0 + j) : 0.f;
+        xl[j] = ((f0 + j) < p.Fin ? __ldg(xfrow + f0 + j) : 0.f) * kLn2;
+        q[j] = fmaf(a1[j], uu[j], c1[j]);
 #pragma unroll
-        for (int c = 0; c < CP; ++c) w1[j][c] = __ldg(p.W1y[k] + (size_t)(f0 + j) * CP + c);
+        for (int c = 0; c < CP; ++c) pc[j][c] = a1[j] * __ldg(p.W1y[k] + (size_t)(f0 + j) * CP + c);  // padded classes: 0
       }
     }
-    for (int dl = 0; dl < nd; ++dl) {
+    T16* hrow = reinterpret_cast<T16*>(p.h1) + ((size_t)k * p.rows_pad + (size_t)n * p.D + d0) * p.Fp + f0;
+    for (int dl = 0; dl < nd; ++dl, hrow += p.Fp) {
       float yv[CP];
 #pragma unroll
-      for (int c = 0; c < CP; ++c) yv[c] = c < C ? sY[dl * CP + c] : 0.f;
+      for (int c = 0; c < CP; ++c) yv[c] = sY[dl * CP + c];   // padded classes hold 0
       float hv[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float lin = uu[j];
+        float v2 = q[j];
 #pragma unroll
-        for (int c = 0; c < CP; ++c) lin = fmaf(w1[j][c], yv[c], lin);
-        hv[j] = softplus_log2dom(fmaf(a1[j], lin, c1[j])) * xx[j];
+        for (int c = 0; c < CP; ++c) v2 = fmaf(pc[j][c], yv[c], v2);
+        const float t = v2 > kSoftplusThreshold * kLog2e ? v2 : lg2_approx(1.0f + ex2_approx(v2));
+        hv[j] = t * xl[j];
       }
       uint4 o;
       o.x = Pack16<T16>::pack(hv[0], hv[1]);
       o.y = Pack16<T16>::pack(hv[2], hv[3]);
       o.z = Pack16<T16>::pack(hv[4], hv[5]);
       o.w = Pack16<T16>::pack(hv[6], hv[7]);
-      const size_t grow = (size_t)k * p.rows_pad + (size_t)n * p.D + d0 + dl;
-      *reinterpret_cast<uint4*>(reinterpret_cast<T16*>(p.h1) + grow * p.Fp + f0) = o;
+      *reinterpret_cast<uint4*>(hrow) = o;
     }
   }
 }
@@ -823,7 +1046,7 @@ size_t tensor_gemm_smem_bytes(int Cp) {
   static_assert(GemmCfg<1>::kStages * GemmCfg<1>::kStageBytes == GemmCfg<2>::kStages * GemmCfg<2>::kStageBytes,
                 "both pipeline geometries use the same ring size");
   return 1024 /*alignment slack*/ + (size_t)GemmCfg<1>::kStages * GemmCfg<1>::kStageBytes +
-         sizeof(float) * BN * (2 + Cp) + sizeof(GemmBarriers);
+         sizeof(float) * (BN * (2 + Cp) + BM * Cp) + sizeof(GemmBarriers);
 }
 
 // 1 = cta_group::1 tiles of 128 rows, 2 = CTA pairs (cta_group::2) on 256-row tiles.  Pairs halve the
@@ -849,7 +1072,10 @@ struct TilePlan {
 // moves 72 KB per K block against 80 KB for a full pair tile, so it is only ~15 % cheaper although it does
 // half the math.  Per-unit quotas come from longest-processing-time assignment; the canonical sequence is
 // then dealt to the least-loaded unit that still has quota for that tile kind, which keeps neighbours in time.
-TilePlan plan_tiles(int K, int rows, int NB, int ctas, int max_units) {
+// row_major: (member, row tile, N tile) -- the NB column tiles of a row group are adjacent, i.e. run at the same
+// time on NB different units (needed by the fused tail + head, which waits for the whole group); otherwise
+// (member, N tile, row tile).
+TilePlan plan_tiles(int K, int rows, int NB, int ctas, int max_units, bool row_major = false) {
   TilePlan tp;
   tp.ctas = ctas;
   tp.tile_rows = BM * ctas;
@@ -880,15 +1106,17 @@ TilePlan plan_tiles(int K, int rows, int NB, int ctas, int max_units) {
   tp.table.assign((size_t)U * tp.stride, -1);
   std::vector<int> fill(U, 0);
   std::fill(load.begin(), load.end(), 0);
+  const int MB = tp.n_full + tp.has_half;
   for (int k = 0; k < K; ++k)
-    for (int nb = 0; nb < NB; ++nb)
-      for (int mb = 0; mb < tp.n_full + tp.has_half; ++mb) {
-        const int half = (tp.has_half && mb == tp.n_full) ? 1 : 0;
-        const int u = least(half ? qhalf : qfull);
-        (half ? qhalf : qfull)[u] -= 1;
-        load[u] += half ? kCostHalf : kCostFull;
-        tp.table[(size_t)u * tp.stride + fill[u]++] = TileCode::pack(k, nb, mb, half);
-      }
+    for (int o = 0; o < NB * MB; ++o) {
+      const int nb = row_major ? o % NB : o / MB;
+      const int mb = row_major ? o / NB : o % MB;
+      const int half = (tp.has_half && mb == tp.n_full) ? 1 : 0;
+      const int u = least(half ? qhalf : qfull);
+      (half ? qhalf : qfull)[u] -= 1;
+      load[u] += half ? kCostHalf : kCostFull;
+      tp.table[(size_t)u * tp.stride + fill[u]++] = TileCode::pack(k, nb, mb, half);
+    }
   return tp;
 }
 
@@ -921,8 +1149,8 @@ struct TensorChain {
   GemmParams g2{}, g3{};
   TailHeadParams tp{};
   dim3 tgrid;
-  int grid = 0, K = 0, Fp = 0, Cp = 0, slot_base = 0, ctas = 1, ycur = 0;
-  bool pdl = false;
+  int grid = 0, K = 0, Fp = 0, Cp = 0, slot_base = 0, ctas = 1, ycur = 0, g3_launches = 0;
+  bool pdl = false, fuse = false;
   float* ybuf[2] = {nullptr, nullptr};
   bool bf16 = false;
 
@@ -935,7 +1163,7 @@ struct TensorChain {
 
   cudaError_t init(ladine_handle* h_, const ladine_member* const* members_, const ladine_sample_args& a_,
                    const ChainIds& ids, const StepCoef* h_coef_, const TensorWorkspace& ws, int n_slots, int n_traj,
-                   cudaStream_t st_, int64_t* launches, std::string* err) {
+                   cudaStream_t st_, bool single_lane, int64_t* launches, std::string* err) {
     h = h_;
     members = members_;
     a = a_;
@@ -949,18 +1177,29 @@ struct TensorChain {
     const int rows = a.N * a.D;
     ctas = choose_ctas(h, rows);
     pdl = pdl_allowed(h, ctas);
+    // the fused tail + head spins on other CTAs of the same launch: every CTA must be resident, so it is only
+    // used when this chain is the sole lane, and its extra per-column parameters fit in smem up to 8 classes
+    fuse = h->fuse && single_lane && Cp <= 8;
     const int NBt = Fp / BN;
     if ((rows + BM - 1) / BM > 4096 || NBt > 1024) {
       *err = "too many rows per member for one launch group (max 524288 chains): tile the images (NestedEnsemble does)";
       return cudaErrorInvalidValue;
     }
     const TilePlan plan = plan_tiles(K, rows, NBt, ctas, h->sm_count / ctas);
+    const TilePlan plan3 = fuse ? plan_tiles(K, rows, NBt, ctas, h->sm_count / ctas, /*row_major=*/true) : plan;
     const int rows_pad = plan.rows_pad;
     const size_t m_total = (size_t)K * rows_pad;
+    const size_t sched_half = sched_bytes_bound(K, rows, NBt) / (2 * sizeof(int32_t));  // ints per table
+    int32_t* sched3 = ws.sched + sched_half;
 
     cudaError_t e = resolve_encode(h, err);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyAsync(ws.sched, plan.table.data(), plan.table.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(sched3, plan3.table.data(), plan3.table.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+    const int mblk_total = plan.n_full + plan.has_half;
+    if (e == cudaSuccess && fuse)
+      e = cudaMemsetAsync(ws.arrivals, 0, sizeof(int) * (size_t)K * mblk_total * ctas, st);
     if (e != cudaSuccess) return e;
     if (!make_tmap(h, &g2.tmA, ws.h1, m_total, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
     if (!make_tmap(h, &g3.tmA, ws.h2, m_total, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
@@ -979,7 +1218,13 @@ struct TensorChain {
       g->sched_stride = plan.stride;
       g->idesc = make_idesc(bf16, ctas);
       g->idesc_half = make_idesc(bf16, 1);  // M = 128 across the pair
+      g->fuse = 0;
     }
+    g3.sched = sched3;
+    g3.sched_stride = plan3.stride;
+    g3.fuse = fuse ? 1 : 0;
+    g3.mblk_total = mblk_total;
+    g3.group_arrivals = ws.arrivals;
     g2.h_out = ws.h2;
     g3.part = ws.part;
     grid = plan.units * ctas;
@@ -1045,11 +1290,6 @@ struct TensorChain {
       e = launch_gemm<2>(g2, grid, bf16, Cp, ctas, pdl, st);
     }
     if (e != cudaSuccess) return e;
-    {
-      ProfSpan ps(h, st, 1);
-      e = launch_gemm<3>(g3, grid, bf16, Cp, ctas, pdl, st);
-    }
-    if (e != cudaSuccess) return e;
     tp.coef = h_coef[t];
     tp.t = t;
     tp.slot = slot_base + (a.t_first - t);
@@ -1059,14 +1299,26 @@ struct TensorChain {
     tp.y_prev = ybuf[ycur];
     tp.y_next = ybuf[ycur ^ 1];
     ycur ^= 1;
+    if (!last) set_head_rows(t - 1);
+    if (fuse) {
+      g3.th = tp;
+      g3.do_head = last ? 0 : 1;
+      g3.arrivals_target = (Fp / BN) * (++g3_launches);
+      {
+        ProfSpan ps(h, st, 1);
+        e = launch_gemm<3>(g3, grid, bf16, Cp, ctas, pdl, st);
+      }
+      if (e == cudaSuccess) *launches += 2;
+      return e;
+    }
+    {
+      ProfSpan ps(h, st, 1);
+      e = launch_gemm<3>(g3, grid, bf16, Cp, ctas, pdl, st);
+    }
+    if (e != cudaSuccess) return e;
     {
       ProfSpan ps(h, st, 2);
-      if (last) {
-        e = launch_tail<kFinal>(tp, tgrid, bf16, Cp, pdl, st);
-      } else {
-        set_head_rows(t - 1);
-        e = launch_tail<kMid>(tp, tgrid, bf16, Cp, pdl, st);
-      }
+      e = last ? launch_tail<kFinal>(tp, tgrid, bf16, Cp, pdl, st) : launch_tail<kMid>(tp, tgrid, bf16, Cp, pdl, st);
     }
     if (e == cudaSuccess) *launches += 3;
     return e;
@@ -1075,9 +1327,10 @@ struct TensorChain {
 
 TensorChain* tensor_chain_create(ladine_handle* h, const ladine_member* const* members, const ladine_sample_args& a,
                                  const ChainIds& ids, const StepCoef* h_coef, const TensorWorkspace& ws, int n_slots,
-                                 int n_traj, cudaStream_t st, int64_t* launches, std::string* err, cudaError_t* status) {
+                                 int n_traj, cudaStream_t st, bool single_lane, int64_t* launches, std::string* err,
+                                 cudaError_t* status) {
   TensorChain* c = new TensorChain();
-  *status = c->init(h, members, a, ids, h_coef, ws, n_slots, n_traj, st, launches, err);
+  *status = c->init(h, members, a, ids, h_coef, ws, n_slots, n_traj, st, single_lane, launches, err);
   if (*status != cudaSuccess) {
     delete c;
     return nullptr;

@@ -164,7 +164,8 @@ def test_pair_mode_chain_matches_reference_golden(name, pair_mode):
 
 
 def test_pair_mode_equals_single_mode_bitwise():
-    """The two tile geometries accumulate every output element over K in the same order -> identical bits."""
+    """Tile geometry (single CTA / CTA pair + half tiles), lane count and the fused tail+head epilogue all
+    compute every chain with the same arithmetic in the same order -> identical bits (incl. trajectory, probs)."""
     import nested_diffusion_b200 as nd
     from nested_diffusion_b200 import engine
     from nested_diffusion_b200.schedule import coef_table
@@ -178,18 +179,22 @@ def test_pair_mode_equals_single_mode_bitwise():
     alphas, omabs = orc.schedule_tensors(orc.make_beta_schedule("linear", T, 1e-4, 0.02))
     coef = coef_table(alphas, omabs, T)
     outs = {}
-    for ctas, lanes in ((1, 1), (2, 1), (1, 2), (2, 3)):
+    for ctas, lanes, fuse in ((1, 1, 0), (1, 1, 1), (2, 1, 1), (2, 1, 0), (1, 2, 1), (2, 3, 1)):
         engine.set_option(0, "ctas", ctas)
         engine.set_option(0, "lanes", lanes)
+        engine.set_option(0, "fuse", fuse)
         try:
-            outs[(ctas, lanes)] = engine.sample_chains(pms, xf, yh, yh, coef, D, seed=5)["y"].clone()
+            outs[(ctas, lanes, fuse)] = engine.sample_chains(pms, xf, yh, yh, coef, D, seed=5, trajectory=True,
+                                                             temperature=0.2)
         finally:
             engine.set_option(0, "ctas", 0)
             engine.set_option(0, "lanes", 1)
-    ref = outs[(1, 1)]
-    assert torch.isfinite(ref).all()
+            engine.set_option(0, "fuse", 0)
+    ref = outs[(1, 1, 0)]
+    assert torch.isfinite(ref["y"]).all()
     for key, val in outs.items():
-        assert torch.equal(ref, val), key
+        for name in ("y", "traj", "probs"):
+            assert torch.equal(ref[name], val[name]), (key, name)
 
 
 def test_philox_equals_injected_replay_and_is_deterministic():
