@@ -71,17 +71,33 @@ def _prepare(model, x, y_0_hat, y_T_mean, output_detach, precision):
 
 
 def p_sample_loop(model, x, y_0_hat, y_T_mean, n_steps, alphas, one_minus_alphas_bar_sqrt, only_last_sample=False,
-                  input_model_original_version=True, output_detach=True, *, noise=None, seed=None, precision="auto"):
+                  input_model_original_version=True, output_detach=True, *, noise=None, seed=None, precision="auto",
+                  draws=None):
     """Full reverse chain y_T -> y_0, diffusion_utils.py:133-163.
 
     Returns y_0 ``[B, C]`` when ``only_last_sample`` else the list ``[y_T, ..., y_1, y_0]`` of
-    ``n_steps + 1`` tensors, on the model's device, FP32, detached."""
+    ``n_steps + 1`` tensors, on the model's device, FP32, detached.
+
+    ``draws=D`` (keyword-only extension) runs D independent chains per input row in ONE launch -- what the runner
+    obtains with D sequential calls (classification_train_separately.py:770-777) -- and returns ``[D, B, C]``
+    (needs ``only_last_sample=True``; ``noise``, if given, is ``[D, n_steps, B, C]``)."""
     if not input_model_original_version:
         model = model.conditional_model
     pm, xf, yh, mu = _prepare(model, x, y_0_hat, y_T_mean, output_detach, precision)
     coef = coef_table(alphas, one_minus_alphas_bar_sqrt, n_steps)
+    B, Cc = y_0_hat.shape
+    if draws is not None:
+        D = int(draws)
+        if D < 1 or not only_last_sample:
+            raise ValueError("draws= needs draws >= 1 and only_last_sample=True")
+        if noise is not None:
+            if tuple(noise.shape) != (D, n_steps, B, Cc):
+                raise ValueError(f"noise must be [draws={D}, n_steps={n_steps}, {B}, {Cc}]")
+            noise = noise.reshape(1, D, n_steps, B, Cc)
+        elif seed is None:
+            seed = engine.fresh_seed()
+        return engine.sample_chains([pm], xf, yh, mu, coef, D, noise=noise, seed=seed or 0)["y"][0]
     if noise is not None:
-        B, Cc = y_0_hat.shape
         if noise.shape[0] < n_steps or tuple(noise.shape[1:]) != (B, Cc):
             raise ValueError(f"noise must be [n_steps={n_steps}, {B}, {Cc}]")
         noise = noise[:n_steps].reshape(1, 1, n_steps, B, Cc)

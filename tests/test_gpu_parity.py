@@ -505,3 +505,26 @@ def test_shape_matrix_vs_oracle(F, C, guidance, K, N, D, T, prec):
     assert rel_err(got["traj"].cpu(), want) <= tol
     assert torch.equal(got["traj"][:, :, -1], got["y"])
     assert torch.allclose(got["probs"].cpu(), orc.convert_to_prob(got["y"].cpu(), 0.3), atol=2e-6)
+
+
+def test_p_sample_loop_draws_extension():
+    """draws=D in one launch == D sequential reference-style calls fed the same noise."""
+    from nested_diffusion_b200 import diffusion_utils as du
+
+    fx = ChainFixture("small_f128_t50")
+    m = fx.meta
+    sd, x, yhat, noise, alphas, omabs = fx.materialize()
+    model = make_model(m, sd)
+    g = torch.Generator().manual_seed(77)
+    D = 3
+    nz = torch.randn(D, m["T"], m["B"], m["C"], generator=g)
+    nz[0] = noise
+    with torch.no_grad():
+        many = du.p_sample_loop(model, x.cuda(), yhat.cuda(), yhat.cuda(), m["T"], alphas.cuda(), omabs.cuda(),
+                                only_last_sample=True, noise=nz.cuda(), draws=D)
+        assert many.shape == (D, m["B"], m["C"])
+        for d in range(D):
+            one = du.p_sample_loop(model, x.cuda(), yhat.cuda(), yhat.cuda(), m["T"], alphas.cuda(), omabs.cuda(),
+                                   only_last_sample=True, noise=nz[d].cuda())
+            assert torch.equal(many[d], one)
+    assert rel_err(many[0].cpu(), fx["y0"]) <= TOL["fp32"]
