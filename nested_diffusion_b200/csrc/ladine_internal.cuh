@@ -68,12 +68,6 @@ namespace ladine {
 
 inline int cpad_of(int C) { return C <= 2 ? 2 : C <= 4 ? 4 : C <= 8 ? 8 : 16; }
 
-struct RowGeom {
-  int K, N, D;
-  int rows;      // N * D valid rows per member
-  int rows_pad;  // rounded up to the row-tile size
-};
-
 // ---- FP32 SMEM-resident path (ladine_resident.cu) ----
 cudaError_t launch_resident(const ladine_handle* h, const ladine_member* const* members, const ladine_sample_args& a,
                             const ChainIds& ids, const StepCoef* d_coef, float* d_u, int n_slots, int n_traj,
