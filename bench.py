@@ -52,7 +52,8 @@ class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu,"
+         "power.draw,power.limit")
 
     def __init__(self, gpu_index: int):
         self.gpu, self.rows, self.proc = gpu_index, [], None
@@ -74,7 +75,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, watts, limit = [], None, set(), [], None
         for r in self.rows:
             try:
                 clk, mxc, util = float(r[0]), float(r[1]), float(r[6])
@@ -83,12 +84,18 @@ class ClockSampler:
             mx = mxc
             if util >= 50:
                 sm.append(clk)
+                try:   # board power under load: the sampler's evidence for "power-capped, not clock-locked"
+                    watts.append(float(r[7]))
+                    limit = float(r[8])
+                except Exception:
+                    pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         allc = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         return {"sm_mhz": statistics.median(sm) if sm else (statistics.median(allc) if allc else None),
-                "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(self.rows)}
+                "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(self.rows),
+                "power_w": statistics.median(watts) if watts else None, "power_limit_w": limit}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -254,6 +254,14 @@ def sample_chains(members: Sequence[PackedMember], xf: torch.Tensor, y0hat: torc
     y_out = torch.empty((K, D, N, m0.C), dtype=torch.float32, device=dev)
     traj = torch.empty((K, D, n_traj, N, m0.C), dtype=torch.float32, device=dev) if trajectory else None
     probs = torch.empty_like(y_out) if temperature is not None else None
+    if N == 0 or D == 0:
+        # an empty batch is a valid call in the reference (every op is a no-op on [0, C]); nothing to launch
+        out = {"y": y_out}
+        if traj is not None:
+            out["traj"] = traj
+        if probs is not None:
+            out["probs"] = probs
+        return out
 
     a = _capi.SampleArgs()
     a.struct_size = C.sizeof(_capi.SampleArgs)

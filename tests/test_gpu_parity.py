@@ -346,6 +346,27 @@ def test_error_behaviour():
         du.p_sample_loop(model, x.cuda(), yhat.cuda()[:3], yhat.cuda(), m["T"], alphas, omabs)
 
 
+def test_empty_and_single_row_batches():
+    """Edge shapes of the drop-in: an empty batch is a valid call (the reference's ops are no-ops on [0, C]) and a
+    single row must equal the same row sampled inside a larger batch on the same injected noise."""
+    from nested_diffusion_b200 import diffusion_utils as du
+
+    fx = ChainFixture("small_f128_t50")
+    m = fx.meta
+    sd, x, yhat, noise, alphas, omabs = fx.materialize()
+    model = make_model(m, sd)
+    xc, yc, nc = x.cuda(), yhat.cuda(), noise.cuda()
+    with torch.no_grad():
+        y0 = du.p_sample_loop(model, xc[:0], yc[:0], yc[:0], m["T"], alphas, omabs, only_last_sample=True)
+        assert tuple(y0.shape) == (0, m["C"]) and y0.dtype == torch.float32 and y0.is_cuda
+        seq = du.p_sample_loop(model, xc[:0], yc[:0], yc[:0], m["T"], alphas, omabs)
+        assert len(seq) == m["T"] + 1 and all(tuple(s.shape) == (0, m["C"]) for s in seq)
+        full = du.p_sample_loop(model, xc, yc, yc, m["T"], alphas, omabs, only_last_sample=True, noise=nc)
+        one = du.p_sample_loop(model, xc[2:3], yc[2:3], yc[2:3], m["T"], alphas, omabs, only_last_sample=True,
+                               noise=nc[:, 2:3])
+        assert rel_err(one[0].cpu(), full[2].cpu()) <= 1e-6   # rows are independent: same arithmetic per row
+
+
 @pytest.mark.slow
 @pytest.mark.parametrize("name", [n for n in names("chain") if Fixture(n).meta["F"] == 4096])
 def test_shipped_trunk_width_full_chain(name):
