@@ -151,7 +151,9 @@ uint64_t ladine_workspace_bytes(const ladine_handle* h);
  *   "pair_gain_permille": measured per-tile speed ratio pair/single used by the auto choice (default 1080);
  *   "pdl" (0 default | 1): programmatic dependent launch, applied to single-CTA chains only;
  *   "fuse" (0 default | 1): run the tail + head of each reverse step inside the layer-3 GEMM kernel (helper warps
- *       gated by per-row-group arrival counters) instead of a separate kernel; bitwise identical results. */
+ *       gated by per-row-group arrival counters) instead of a separate kernel; bitwise identical results;
+ *   "tail_vec" (0 auto | 4 | 8): features per thread of the tail/head kernel; auto picks the width whose CTA
+ *       count quantises best into waves of resident CTAs (results are identical either way). */
 int ladine_set_option(ladine_handle* h, const char* key, int64_t value);
 
 /* Optional per-kernel timing of the tensor-core path.  When enabled, ladine_sample brackets every

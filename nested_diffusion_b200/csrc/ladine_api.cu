@@ -584,6 +584,11 @@ int ladine_set_option(ladine_handle* h, const char* key, int64_t value) {
     h->ctas = (int)value;
     return LADINE_OK;
   }
+  if (strcmp(key, "tail_vec") == 0) {
+    if (value != 0 && value != 4 && value != 8) return fail(h, LADINE_ERR_INVALID, "tail_vec must be 0 (auto), 4 or 8");
+    h->tail_vec = (int)value;
+    return LADINE_OK;
+  }
   if (strcmp(key, "pair_gain_permille") == 0) {
     if (value < 500 || value > 2000) return fail(h, LADINE_ERR_INVALID, "pair_gain_permille must be in [500, 2000]");
     h->pair_gain = value / 1000.0;

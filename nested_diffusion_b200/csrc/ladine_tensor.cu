@@ -740,11 +740,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
 // tail (posterior update of step t) + head (lin1 of step t-1)
 // ------------------------------------------------------------------------------------------
 constexpr int kTailThreads = 128;
-constexpr int kTailCols = kTailThreads * 8;  // features per CTA: 8 per thread
 constexpr int kTailMaxRows = 32;  // draws handled per CTA
 
-template <int MODE, typename T16, int CP>
+// VEC = features per thread (8 or 4): the host picks the one whose CTA count quantises best into waves of resident
+// CTAs (config 2 with VEC = 8: 1400 CTAs on 148 x 7 slots = 1.35 waves, i.e. a second wave that is one third full).
+template <int MODE, typename T16, int CP, int VEC>
 __global__ void __launch_bounds__(kTailThreads) tailhead_kernel(const __grid_constant__ TailHeadParams p) {
+  constexpr int kTailCols = kTailThreads * VEC;   // features per CTA
   __shared__ float sY[kTailMaxRows * CP];
   // grid.x = N * colsplit: CTA (n, cs) produces features [cs * kTailCols, (cs+1) * kTailCols) of image n's draws.
   // Every column split recomputes the (tiny) tail; split 0 alone publishes y / outputs.
@@ -821,26 +823,26 @@ __global__ void __launch_bounds__(kTailThreads) tailhead_kernel(const __grid_con
   if (MODE == kFinal) return;
 
   // ---------------- head: h1 of the next step for the same rows ----------------
-  // thread owns 8 consecutive features; their per-column constants stay in registers across draws
+  // thread owns VEC consecutive features; their per-column constants stay in registers across draws
   const float* xfrow = p.xf + ((size_t)k * p.N + n) * p.Fin;
   const float* urow = p.u + ((size_t)k * p.N + n) * p.Fp;
-  for (int f0 = cs * kTailCols + tid * 8; f0 < p.Fp; f0 += p.colsplit * kTailCols) {
+  for (int f0 = cs * kTailCols + tid * VEC; f0 < p.Fp; f0 += p.colsplit * kTailCols) {
     // per-column constants of this step, folded once per CTA:  v2 = sum_c pc[c] * y[c] + q  (log2 domain),
     // h1 = softplus(v2 / log2e) * xf = t * xl  with  t = lg2(1 + 2^v2) (or v2 itself when large), xl = xf * ln2
-    float q[8], xl[8], pc[8][CP];
+    float q[VEC], xl[VEC], pc[VEC][CP];
     {
-      float a1[8], c1[8], uu[8];
-      const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.A1[k] + f0));
-      const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.A1[k] + f0 + 4));
-      a1[0] = t0.x; a1[1] = t0.y; a1[2] = t0.z; a1[3] = t0.w; a1[4] = t1.x; a1[5] = t1.y; a1[6] = t1.z; a1[7] = t1.w;
-      const float4 q0 = __ldg(reinterpret_cast<const float4*>(p.C1[k] + f0));
-      const float4 q1 = __ldg(reinterpret_cast<const float4*>(p.C1[k] + f0 + 4));
-      c1[0] = q0.x; c1[1] = q0.y; c1[2] = q0.z; c1[3] = q0.w; c1[4] = q1.x; c1[5] = q1.y; c1[6] = q1.z; c1[7] = q1.w;
-      const float4 u0 = __ldg(reinterpret_cast<const float4*>(urow + f0));
-      const float4 u1 = __ldg(reinterpret_cast<const float4*>(urow + f0 + 4));
-      uu[0] = u0.x; uu[1] = u0.y; uu[2] = u0.z; uu[3] = u0.w; uu[4] = u1.x; uu[5] = u1.y; uu[6] = u1.z; uu[7] = u1.w;
+      float a1[VEC], c1[VEC], uu[VEC];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int v = 0; v < VEC / 4; ++v) {
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.A1[k] + f0) + v);
+        a1[4 * v + 0] = t0.x; a1[4 * v + 1] = t0.y; a1[4 * v + 2] = t0.z; a1[4 * v + 3] = t0.w;
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(p.C1[k] + f0) + v);
+        c1[4 * v + 0] = q0.x; c1[4 * v + 1] = q0.y; c1[4 * v + 2] = q0.z; c1[4 * v + 3] = q0.w;
+        const float4 u0 = __ldg(reinterpret_cast<const float4*>(urow + f0) + v);
+        uu[4 * v + 0] = u0.x; uu[4 * v + 1] = u0.y; uu[4 * v + 2] = u0.z; uu[4 * v + 3] = u0.w;
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
         xl[j] = ((f0 + j) < p.Fin ? __ldg(xfrow + f0 + j) : 0.f) * kLn2;
         q[j] = fmaf(a1[j], uu[j], c1[j]);
 #pragma unroll
@@ -852,21 +854,28 @@ __global__ void __launch_bounds__(kTailThreads) tailhead_kernel(const __grid_con
       float yv[CP];
 #pragma unroll
       for (int c = 0; c < CP; ++c) yv[c] = sY[dl * CP + c];   // padded classes hold 0
-      float hv[8];
+      float hv[VEC];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < VEC; ++j) {
         float v2 = q[j];
 #pragma unroll
         for (int c = 0; c < CP; ++c) v2 = fmaf(pc[j][c], yv[c], v2);
         const float t = v2 > kSoftplusThreshold * kLog2e ? v2 : lg2_approx(1.0f + ex2_approx(v2));
         hv[j] = t * xl[j];
       }
-      uint4 o;
-      o.x = Pack16<T16>::pack(hv[0], hv[1]);
-      o.y = Pack16<T16>::pack(hv[2], hv[3]);
-      o.z = Pack16<T16>::pack(hv[4], hv[5]);
-      o.w = Pack16<T16>::pack(hv[6], hv[7]);
-      *reinterpret_cast<uint4*>(hrow) = o;
+      if (VEC == 8) {
+        uint4 o;
+        o.x = Pack16<T16>::pack(hv[0], hv[1]);
+        o.y = Pack16<T16>::pack(hv[2], hv[3]);
+        o.z = Pack16<T16>::pack(hv[VEC - 4], hv[VEC - 3]);
+        o.w = Pack16<T16>::pack(hv[VEC - 2], hv[VEC - 1]);
+        *reinterpret_cast<uint4*>(hrow) = o;
+      } else {
+        uint2 o;
+        o.x = Pack16<T16>::pack(hv[0], hv[1]);
+        o.y = Pack16<T16>::pack(hv[2], hv[3]);
+        *reinterpret_cast<uint2*>(hrow) = o;
+      }
     }
   }
 }
@@ -978,9 +987,9 @@ cudaError_t launch_gemm(const GemmParams& p, int grid, bool bf16, int Cp, int ct
               : launch_gemm_c<LAYER, __half>(p, grid, Cp, ctas, pdl, st);
 }
 
-template <int MODE, typename T16, int CP>
+template <int MODE, typename T16, int CP, int VEC>
 cudaError_t launch_tail_t(const TailHeadParams& p, dim3 grid, bool pdl, cudaStream_t st) {
-  auto kern = tailhead_kernel<MODE, T16, CP>;
+  auto kern = tailhead_kernel<MODE, T16, CP, VEC>;
   // same shared-memory carveout as the GEMM kernels, so the SMs are not reconfigured at every kernel boundary
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
@@ -998,10 +1007,14 @@ cudaError_t launch_tail_t(const TailHeadParams& p, dim3 grid, bool pdl, cudaStre
 }
 
 template <int MODE>
-cudaError_t launch_tail(const TailHeadParams& p, dim3 grid, bool bf16, int Cp, bool pdl, cudaStream_t st) {
-#define LADINE_TAIL_CASE(CPV)                                                              \
-  case CPV:                                                                                \
-    return bf16 ? launch_tail_t<MODE, __nv_bfloat16, CPV>(p, grid, pdl, st) : launch_tail_t<MODE, __half, CPV>(p, grid, pdl, st);
+cudaError_t launch_tail(const TailHeadParams& p, dim3 grid, bool bf16, int Cp, int vec, bool pdl, cudaStream_t st) {
+#define LADINE_TAIL_CASE(CPV)                                                                                     \
+  case CPV:                                                                                                       \
+    if (vec == 4)                                                                                                 \
+      return bf16 ? launch_tail_t<MODE, __nv_bfloat16, CPV, 4>(p, grid, pdl, st)                                  \
+                  : launch_tail_t<MODE, __half, CPV, 4>(p, grid, pdl, st);                                        \
+    return bf16 ? launch_tail_t<MODE, __nv_bfloat16, CPV, 8>(p, grid, pdl, st)                                    \
+                : launch_tail_t<MODE, __half, CPV, 8>(p, grid, pdl, st);
   switch (Cp) {
     LADINE_TAIL_CASE(2)
     LADINE_TAIL_CASE(4)
@@ -1010,6 +1023,26 @@ cudaError_t launch_tail(const TailHeadParams& p, dim3 grid, bool bf16, int Cp, b
   }
 #undef LADINE_TAIL_CASE
   return cudaErrorInvalidValue;
+}
+
+// resident CTAs per SM of the mid-step tail/head kernel (what the wave model in TensorChain::init needs)
+template <int VEC>
+int tail_occupancy(bool bf16, int Cp) {
+  int occ = 0;
+#define LADINE_OCC_CASE(CPV)                                                                                         \
+  case CPV:                                                                                                          \
+    if (bf16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tailhead_kernel<kMid, __nv_bfloat16, CPV, VEC>,    \
+                                                            kTailThreads, 0);                                        \
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tailhead_kernel<kMid, __half, CPV, VEC>, kTailThreads, 0); \
+    break;
+  switch (Cp) {
+    LADINE_OCC_CASE(2)
+    LADINE_OCC_CASE(4)
+    LADINE_OCC_CASE(8)
+    LADINE_OCC_CASE(16)
+  }
+#undef LADINE_OCC_CASE
+  return occ > 0 ? occ : 1;
 }
 
 struct ProfSpan {
@@ -1149,7 +1182,7 @@ struct TensorChain {
   GemmParams g2{}, g3{};
   TailHeadParams tp{};
   dim3 tgrid;
-  int grid = 0, K = 0, Fp = 0, Cp = 0, slot_base = 0, ctas = 1, ycur = 0, g3_launches = 0;
+  int grid = 0, K = 0, Fp = 0, Cp = 0, slot_base = 0, ctas = 1, ycur = 0, g3_launches = 0, tail_vec = 8;
   bool pdl = false, fuse = false;
   float* ybuf[2] = {nullptr, nullptr};
   bool bf16 = false;
@@ -1259,7 +1292,24 @@ struct TensorChain {
     tp.n_slots = n_slots;
     tp.n_traj = n_traj;
     tp.dchunk = a.D < kTailMaxRows ? a.D : kTailMaxRows;
-    tp.colsplit = (Fp + kTailCols - 1) / kTailCols;
+    {
+      // features per thread: the SMs are throughput-bound, so a launch costs ~ ceil(waves) x (resident CTAs x work per
+      // CTA); pick the width whose CTA count quantises best (16 = the per-CTA tail, in element-rows per thread)
+      const long long dchunks = (a.D + tp.dchunk - 1) / tp.dchunk;
+      double best = 0;
+      for (int vec : {8, 4}) {
+        if (h->tail_vec != 0 && h->tail_vec != vec) continue;   // "tail_vec" option: force a width (A/B timing)
+        const int occ = vec == 8 ? tail_occupancy<8>(bf16, Cp) : tail_occupancy<4>(bf16, Cp);
+        const int cs = (Fp + kTailThreads * vec - 1) / (kTailThreads * vec);
+        const long long ctas = (long long)a.N * cs * K * dchunks, slots = (long long)occ * h->sm_count;
+        const double cost = (double)((ctas + slots - 1) / slots) * occ * (vec * tp.dchunk + 16);
+        if (best == 0 || cost < best * 0.97) {   // 8 features per thread unless 4 is clearly better
+          best = cost;
+          tail_vec = vec;
+          tp.colsplit = cs;
+        }
+      }
+    }
     tgrid = dim3(a.N * tp.colsplit, K, (a.D + tp.dchunk - 1) / tp.dchunk);
     slot_base = a.y_init ? 0 : 1;
 
@@ -1271,7 +1321,7 @@ struct TensorChain {
     tp.y_prev = ybuf[ycur];
     tp.y_next = ybuf[ycur ^ 1];
     ycur ^= 1;
-    e = launch_tail<kInit>(tp, tgrid, bf16, Cp, pdl, st);
+    e = launch_tail<kInit>(tp, tgrid, bf16, Cp, tail_vec, pdl, st);
     if (e == cudaSuccess) ++*launches;
     return e;
   }
@@ -1318,7 +1368,8 @@ struct TensorChain {
     if (e != cudaSuccess) return e;
     {
       ProfSpan ps(h, st, 2);
-      e = last ? launch_tail<kFinal>(tp, tgrid, bf16, Cp, pdl, st) : launch_tail<kMid>(tp, tgrid, bf16, Cp, pdl, st);
+      e = last ? launch_tail<kFinal>(tp, tgrid, bf16, Cp, tail_vec, pdl, st)
+               : launch_tail<kMid>(tp, tgrid, bf16, Cp, tail_vec, pdl, st);
     }
     if (e == cudaSuccess) *launches += 3;
     return e;

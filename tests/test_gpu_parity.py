@@ -2,8 +2,9 @@
 
 Tolerances (max-abs relative to max(1, ||y_ref||_inf); stated here, used below):
   FP32 SMEM-resident path ........ 1e-5   vs the reference's own p_sample_loop output
-  FP16 tensor path ............... 5e-4   vs the reference;  2e-5 vs the oracle's FP16-operand emulation
-  BF16 tensor path ............... 4e-3   vs the reference;  2e-5 vs the oracle's BF16-operand emulation
+  FP16 tensor path ............... 1e-4   vs the reference;  2e-5 vs the oracle's FP16-operand emulation
+  BF16 tensor path ............... 5e-4   vs the reference;  2e-4 vs the oracle's BF16-operand emulation
+(the SURVEY.md §8d bars; measured: FP16 <= 3.4e-5, BF16 <= 2.7e-4 over every fixture -- profiles/r01_parity_report.csv)
 and argmax labels identical wherever the reference's top-2 margin exceeds the tolerance band.
 """
 import argparse
@@ -16,7 +17,7 @@ from tests.golden_util import ChainFixture, EnsembleFixture, Fixture, names, rel
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-5, "fp16": 5e-4, "bf16": 4e-3}
+TOL = {"fp32": 1e-5, "fp16": 1e-4, "bf16": 5e-4}
 TOL_EMU = 2e-5
 ODT = {"fp16": torch.float16, "bf16": torch.bfloat16}
 
