@@ -745,7 +745,7 @@ constexpr int kTailMaxRows = 32;  // draws handled per CTA
 // VEC = features per thread (8 or 4): the host picks the one whose CTA count quantises best into waves of resident
 // CTAs (config 2 with VEC = 8: 1400 CTAs on 148 x 7 slots = 1.35 waves, i.e. a second wave that is one third full).
 template <int MODE, typename T16, int CP, int VEC>
-__global__ void __launch_bounds__(kTailThreads) tailhead_kernel(const __grid_constant__ TailHeadParams p) {
+__global__ void __launch_bounds__(kTailThreads, (CP <= 4 ? 8 : 1)) tailhead_kernel(const __grid_constant__ TailHeadParams p) {
   constexpr int kTailCols = kTailThreads * VEC;   // features per CTA
   __shared__ float sY[kTailMaxRows * CP];
   // grid.x = N * colsplit: CTA (n, cs) produces features [cs * kTailCols, (cs+1) * kTailCols) of image n's draws.
