@@ -152,6 +152,9 @@ uint64_t ladine_workspace_bytes(const ladine_handle* h);
  *   "pdl" (0 default | 1): programmatic dependent launch, applied to single-CTA chains only;
  *   "fuse" (0 default | 1): run the tail + head of each reverse step inside the layer-3 GEMM kernel (helper warps
  *       gated by per-row-group arrival counters) instead of a separate kernel; bitwise identical results;
+ *   "order" (0 auto | 1 | 2): GEMM tile order -- N-tile-major (a W tile stays hot while a member's rows stream past
+ *       it) or row-major (the activations are read once; chosen automatically when a member's activations
+ *       exceed 32 MiB and would otherwise be re-read from HBM for every N tile); results are identical;
  *   "tail_vec" (0 auto | 4 | 8): features per thread of the tail/head kernel; auto picks the width whose CTA
  *       count quantises best into waves of resident CTAs (results are identical either way). */
 int ladine_set_option(ladine_handle* h, const char* key, int64_t value);

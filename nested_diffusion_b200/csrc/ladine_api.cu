@@ -584,6 +584,11 @@ int ladine_set_option(ladine_handle* h, const char* key, int64_t value) {
     h->ctas = (int)value;
     return LADINE_OK;
   }
+  if (strcmp(key, "order") == 0) {
+    if (value < 0 || value > 2) return fail(h, LADINE_ERR_INVALID, "order must be 0 (auto), 1 (N-tile-major) or 2 (row-major)");
+    h->order = (int)value;
+    return LADINE_OK;
+  }
   if (strcmp(key, "tail_vec") == 0) {
     if (value != 0 && value != 4 && value != 8) return fail(h, LADINE_ERR_INVALID, "tail_vec must be 0 (auto), 4 or 8");
     h->tail_vec = (int)value;

@@ -39,6 +39,9 @@ constexpr int kEpiWarps = kEpiThreads / 32;   // warps 0..3: epilogue (TMEM lane
 constexpr int kHelperWarp0 = 4;               // warps 4..7: fused tail + head jobs (layer 3), idle otherwise
 constexpr int kProducerWarp = 8;
 constexpr int kMmaWarp = 9;
+// a member's activations above this size no longer survive in the 126 MB L2 between N tiles (with W and the
+// layer's output also passing through): switch the tile order to row-major
+constexpr size_t kRowMajorActBytes = (size_t)32 << 20;
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -1218,8 +1221,14 @@ struct TensorChain {
       *err = "too many rows per member for one launch group (max 524288 chains): tile the images (NestedEnsemble does)";
       return cudaErrorInvalidValue;
     }
-    const TilePlan plan = plan_tiles(K, rows, NBt, ctas, h->sm_count / ctas);
-    const TilePlan plan3 = fuse ? plan_tiles(K, rows, NBt, ctas, h->sm_count / ctas, /*row_major=*/true) : plan;
+    // Tile order.  N-tile-major keeps one 2 MiB W tile hot while all row tiles of a member stream past it: right while
+    // a member's activations (rows x Fp 16-bit) stay in L2, but beyond that every N tile re-reads them from HBM
+    // (F/256 = 16 passes at the shipped width).  Row-major runs the F/256 column tiles of a few row tiles together:
+    // the activations are read once and the member's 32 MiB W cycles through L2.  "order" option: 0 auto, 1 / 2 force.
+    const size_t act_bytes = (size_t)((rows + BM - 1) / BM) * BM * Fp * 2;
+    const bool row_major = h->order == 2 || (h->order == 0 && act_bytes > kRowMajorActBytes);
+    const TilePlan plan = plan_tiles(K, rows, NBt, ctas, h->sm_count / ctas, row_major);
+    const TilePlan plan3 = (fuse && !row_major) ? plan_tiles(K, rows, NBt, ctas, h->sm_count / ctas, /*row_major=*/true) : plan;
     const int rows_pad = plan.rows_pad;
     const size_t m_total = (size_t)K * rows_pad;
     const size_t sched_half = sched_bytes_bound(K, rows, NBt) / (2 * sizeof(int32_t));  // ints per table

@@ -165,8 +165,8 @@ def test_pair_mode_chain_matches_reference_golden(name, pair_mode):
 
 
 def test_pair_mode_equals_single_mode_bitwise():
-    """Tile geometry (single CTA / CTA pair + half tiles), lane count and the fused tail+head epilogue all
-    compute every chain with the same arithmetic in the same order -> identical bits (incl. trajectory, probs)."""
+    """Tile geometry (single CTA / CTA pair + half tiles), tile order (N-tile-major / row-major), lane count and the
+    fused tail+head epilogue all compute every chain with the same arithmetic in the same order -> identical bits (incl. trajectory, probs)."""
     import nested_diffusion_b200 as nd
     from nested_diffusion_b200 import engine
     from nested_diffusion_b200.schedule import coef_table
@@ -180,18 +180,21 @@ def test_pair_mode_equals_single_mode_bitwise():
     alphas, omabs = orc.schedule_tensors(orc.make_beta_schedule("linear", T, 1e-4, 0.02))
     coef = coef_table(alphas, omabs, T)
     outs = {}
-    for ctas, lanes, fuse in ((1, 1, 0), (1, 1, 1), (2, 1, 1), (2, 1, 0), (1, 2, 1), (2, 3, 1)):
+    for ctas, lanes, fuse, order in ((1, 1, 0, 1), (1, 1, 1, 0), (2, 1, 1, 0), (2, 1, 0, 1), (1, 2, 1, 0), (2, 3, 1, 0),
+                                     (1, 1, 0, 2), (2, 1, 0, 2), (1, 2, 1, 2)):
         engine.set_option(0, "ctas", ctas)
         engine.set_option(0, "lanes", lanes)
         engine.set_option(0, "fuse", fuse)
+        engine.set_option(0, "order", order)
         try:
-            outs[(ctas, lanes, fuse)] = engine.sample_chains(pms, xf, yh, yh, coef, D, seed=5, trajectory=True,
+            outs[(ctas, lanes, fuse, order)] = engine.sample_chains(pms, xf, yh, yh, coef, D, seed=5, trajectory=True,
                                                              temperature=0.2)
         finally:
             engine.set_option(0, "ctas", 0)
             engine.set_option(0, "lanes", 1)
             engine.set_option(0, "fuse", 0)
-    ref = outs[(1, 1, 0)]
+            engine.set_option(0, "order", 0)
+    ref = outs[(1, 1, 0, 1)]
     assert torch.isfinite(ref["y"]).all()
     for key, val in outs.items():
         for name in ("y", "traj", "probs"):

@@ -18,6 +18,8 @@ fuse = int(sys.argv[10]) if len(sys.argv) > 10 else 0
 engine.set_option(0, "fuse", fuse)
 tail_vec = int(sys.argv[11]) if len(sys.argv) > 11 else 0
 engine.set_option(0, "tail_vec", tail_vec)
+order = int(sys.argv[12]) if len(sys.argv) > 12 else 0
+engine.set_option(0, "order", order)
 C = 2
 dev = torch.device("cuda")
 g = torch.Generator(device="cuda").manual_seed(0)
@@ -55,5 +57,5 @@ for it in range(4):
     flops = K * N * D * T * (4.0 * F * F + 6 * F * C)
     print(f"K={K} N={N} D={D} F={F} T={T} {members[0].precision}: {ms:.2f} ms  ({ms/T*1e3:.1f} us/step)  "
           f"{flops/ms/1e9:.1f} TFLOP/s  samples/s(T=1000 equiv)={K*N*D/(ms/1e3)*T/1000:.0f}  host enqueue {1e3*(t1-t0):.1f} ms  "
-          f"finite={bool(torch.isfinite(y).all())} launches={engine.last_launches(0)} lanes={lanes} ctas={ctas} pdl={pdl} fuse={fuse} tail_vec={tail_vec}")
+          f"finite={bool(torch.isfinite(y).all())} launches={engine.last_launches(0)} lanes={lanes} ctas={ctas} pdl={pdl} fuse={fuse} tail_vec={tail_vec} order={order}")
 print("profile:", engine.get_profile(0))
