@@ -146,8 +146,10 @@ uint64_t ladine_workspace_bytes(const ladine_handle* h);
 /* Tuning knobs (tensor-core path).
  *   "lanes" (1..4, default 1): groups of members advanced concurrently on internal streams (forked from /
  *       joined to the caller's stream) so one group's tail/head kernel hides under another group's GEMMs;
- *   "ctas" (0 auto | 1 | 2): GEMM tile geometry -- single CTAs (cta_group::1, 128x256 tiles) or CTA pairs
- *       (cta_group::2, 256x256 tiles + 2x64-row half tiles); auto picks pairs when the rows pad well;
+ *   "ctas" (0 auto | 1 | 2 | 3): GEMM tile geometry -- single CTAs (cta_group::1, 128x256 tiles), CTA pairs
+ *       (cta_group::2, 256x256 tiles + 2x64-row half tiles) or slim single-CTA 128x128 tiles; auto picks pairs
+ *       when the rows pad well and slim tiles when the call is so small that twice as many tiles still fit the
+ *       SMs in one round; all geometries give bit-identical results;
  *   "pair_gain_permille": measured per-tile speed ratio pair/single used by the auto choice (default 1080);
  *   "pdl" (0 default | 1): programmatic dependent launch, applied to single-CTA chains only;
  *   "fuse" (0 default | 1): run the tail + head of each reverse step inside the layer-3 GEMM kernel (helper warps

@@ -468,7 +468,7 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
     o_h1 = lo; lo = align_up(lo + m_total * Fp * 2, 1024);
     o_h2 = lo; lo = align_up(lo + m_total * Fp * 2, 1024);
     o_part = lo; lo = align_up(lo + m_total * (Fp / 256) * 2 * Cp * 4, 1024);
-    o_sched = lo; lo = align_up(lo + sched_bytes_bound(gmax, rows, Fp / 256), 1024);
+    o_sched = lo; lo = align_up(lo + sched_bytes_bound(gmax, rows, Fp / 128), 1024);
     o_arr = lo; lo = align_up(lo + (uint64_t)gmax * ((rows + 127) / 128 + 1) * 2 * sizeof(int), 1024);
     o_y = lo; lo = align_up(lo + 2 * m_total * Cp * 4, 1024);
   }
@@ -580,7 +580,7 @@ int ladine_set_option(ladine_handle* h, const char* key, int64_t value) {
     return LADINE_OK;
   }
   if (strcmp(key, "ctas") == 0) {
-    if (value < 0 || value > 2) return fail(h, LADINE_ERR_INVALID, "ctas must be 0 (auto), 1 or 2");
+    if (value < 0 || value > 3) return fail(h, LADINE_ERR_INVALID, "ctas must be 0 (auto), 1, 2 or 3 (slim tiles)");
     h->ctas = (int)value;
     return LADINE_OK;
   }
@@ -684,7 +684,7 @@ int ladine_debug_layer(ladine_handle* h, const ladine_member* member, int layer,
   if (member->precision == LADINE_PREC_FP32) return fail(h, LADINE_ERR_UNSUPPORTED, "debug layer is for the tensor path");
   if ((layer == 2 && !h_out) || (layer == 3 && !part)) return fail(h, LADINE_ERR_INVALID, "missing output buffer");
   DeviceGuard guard(h->device);
-  int rc = ensure_workspace(h, sched_bytes_bound(1, rows, member->Fp / 256));
+  int rc = ensure_workspace(h, sched_bytes_bound(1, rows, member->Fp / 128));
   if (rc != LADINE_OK) return rc;
   std::string err;
   cudaError_t e = launch_debug_layer(h, member, layer, t, h_in, rows, h_out, part, static_cast<int32_t*>(h->ws),

@@ -211,10 +211,13 @@ struct TileCode {
 
 // pipeline geometry per CTA: CTAS = 1 -> A 128x64 + B 256x64 per stage; CTAS = 2 (cta_group::2, the
 // CTA pair computes a 256x256 tile) -> A 128x64 + the CTA's half of B 128x64 per stage, so deeper ring
-template <int CTAS>
+// BNT = tile width: 256, or 128 ("slim" single-CTA tiles for calls too small to fill the SMs with 256-wide tiles:
+// twice as many tiles, each 64 KB instead of 96 KB of shared-memory traffic per K block)
+template <int CTAS, int BNT = BN>
 struct GemmCfg {
-  static constexpr int kStages = CTAS == 1 ? 4 : 6;
-  static constexpr int kBRows = BN / CTAS;
+  static_assert(BNT == 256 || (BNT == 128 && CTAS == 1), "slim tiles are single-CTA only");
+  static constexpr int kStages = (CTAS == 1 && BNT == 256) ? 4 : 6;
+  static constexpr int kBRows = BNT / CTAS;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -434,9 +437,10 @@ __device__ __forceinline__ void fused_tail_head(const TailHeadParams& th, float*
   }
 }
 
-template <int LAYER, typename T16, int CP, int CTAS>
+template <int LAYER, typename T16, int CP, int CTAS, int BNT>
 __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<CTAS>;
+  using Cfg = GemmCfg<CTAS, BNT>;
+  constexpr bool kCanFuse = LAYER == 3 && CP <= 8 && BNT == BN;   // fused tail + head: 256-wide tiles only
   constexpr int kStages = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
   uint8_t* sB = smem + kStages * Cfg::kABytes;           // kStages x 32 (16) KiB
   float* sEpi = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);  // scale[256] shift[256] (W4[CP][256])
   // layer 3: scale[256] | shift[256] | W4[CP][256] | y_next of this CTA's rows [128][CP] (fused tail + head)
-  constexpr int kEpiFloats = LAYER == 3 ? BN * (2 + CP) + BM * CP : 2 * BN;
+  constexpr int kEpiFloats = LAYER == 3 ? BNT * (2 + CP) + BM * CP : 2 * BNT;
   GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(sEpi + kEpiFloats);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -492,7 +496,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
         const TileCode tc(code);
         // a half tile gives each CTA of the pair 64 rows; the 128-row box is still loaded (upper half unused)
         const int arow = tc.member * p.rows_pad + tc.mb * (BM * CTAS) + (int)rank * (tc.half ? BM / 2 : BM);
-        const int brow = tc.nb * BN + (int)rank * Cfg::kBRows;
+        const int brow = tc.nb * BNT + (int)rank * Cfg::kBRows;
         const CUtensorMap* tb = &p.tmB[tc.member];
         for (int kb = 0; kb < p.KB; ++kb) {
           mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u, 0);
@@ -524,7 +528,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(smem_u32(&bars->acc_empty[as]), aphase ^ 1u, 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BNT);
         for (int kb = 0; kb < p.KB; ++kb) {
           mbar_wait(smem_u32(&bars->full[stage]), phase, 2);
           tc_fence_after();
@@ -553,8 +557,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
     const int et = threadIdx.x;              // 0..127
     const int quad = warp;                   // TMEM lane quadrant this warp may access
     float* sScale = sEpi;
-    float* sShift = sEpi + BN;
-    float* sW4 = sEpi + 2 * BN;              // [CP][BN]
+    float* sShift = sEpi + BNT;
+    float* sW4 = sEpi + 2 * BNT;             // [CP][BNT]
     for (int it = 0;; ++it) {
       const int32_t code = __ldg(my_sched + it);
       if (code < 0) break;
@@ -564,26 +568,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       // stage this tile's per-column parameters (independent of the accumulator: issued before the wait)
       {
-        const float* gs = p.scale[member] + nb * BN;
-        const float* gh = p.shift[member] + nb * BN;
-        const float s0 = __ldg(gs + et), s1 = __ldg(gs + et + 128);
-        const float h0 = __ldg(gh + et), h1 = __ldg(gh + et + 128);
+        const float* gs = p.scale[member] + nb * BNT;
+        const float* gh = p.shift[member] + nb * BNT;
+        constexpr int kHi = BNT == 256 ? 128 : 0;   // second column of this thread (none for 128-wide tiles)
+        const float s0 = __ldg(gs + et), s1 = __ldg(gs + et + kHi);
+        const float h0 = __ldg(gh + et), h1 = __ldg(gh + et + kHi);
         float w4v[LAYER == 3 ? 2 * CP : 1];
         if (LAYER == 3) {
 #pragma unroll
           for (int c = 0; c < CP; ++c) {
-            w4v[2 * c] = __ldg(p.W4[member] + (size_t)c * p.Fp + nb * BN + et);
-            w4v[2 * c + 1] = __ldg(p.W4[member] + (size_t)c * p.Fp + nb * BN + et + 128);
+            w4v[2 * c] = __ldg(p.W4[member] + (size_t)c * p.Fp + nb * BNT + et);
+            w4v[2 * c + 1] = __ldg(p.W4[member] + (size_t)c * p.Fp + nb * BNT + et + kHi);
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
-        sScale[et] = s0; sScale[et + 128] = s1;
-        sShift[et] = h0; sShift[et + 128] = h1;
+        sScale[et] = s0; sScale[et + kHi] = s1;
+        sShift[et] = h0; sShift[et + kHi] = h1;
         if (LAYER == 3) {
 #pragma unroll
           for (int c = 0; c < CP; ++c) {
-            sW4[c * BN + et] = w4v[2 * c];
-            sW4[c * BN + et + 128] = w4v[2 * c + 1];
+            sW4[c * BNT + et] = w4v[2 * c];
+            sW4[c * BNT + et + kHi] = w4v[2 * c + 1];
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -600,10 +605,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
                              : tc.mb * (BM * CTAS) + (int)rank * BM + quad * 32 + lane;   // row within the member
       const bool valid = row_m < p.rows;
       const size_t grow = (size_t)member * p.rows_pad + row_m;
-      const uint32_t taddr = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quad * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)(as * BNT) + ((uint32_t)(quad * 32) << 16);
       // lin4 partials are kept per 128-column slot so that every tile geometry sums the same values in the
       // same order (tail kernel: fixed-order sum over 2 * NB slots) -> results do not depend on the geometry
-      const int nslot = half ? 1 : 2;
+      const int nslot = half ? 1 : BNT / 128;
       const int slot0 = half ? (quad >> 1) : 0;
 #pragma unroll 1
       for (int sl = 0; sl < nslot; ++sl) {
@@ -631,7 +636,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
           if (LAYER == 2) {
             if (valid) {
               // 32 consecutive 16-bit outputs of this row = 64 B = two full 32-byte sectors: 256-bit stores
-              T16* dst = reinterpret_cast<T16*>(p.h_out) + grow * p.Fp + nb * BN + ocol;
+              T16* dst = reinterpret_cast<T16*>(p.h_out) + grow * p.Fp + nb * BNT + ocol;
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
                 uint32_t o[8];
@@ -646,7 +651,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
               float e = eacc[c];
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 w = *reinterpret_cast<const float4*>(sW4 + c * BN + ocol + j4 * 4);
+                const float4 w = *reinterpret_cast<const float4*>(sW4 + c * BNT + ocol + j4 * 4);
                 e = fmaf(hcol[4 * j4 + 0], w.x, e);
                 e = fmaf(hcol[4 * j4 + 1], w.y, e);
                 e = fmaf(hcol[4 * j4 + 2], w.z, e);
@@ -657,7 +662,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
           }
         }
         if (LAYER == 3 && valid) {
-          float* dst = p.part + ((grow * p.NB + nb) * 2 + slot) * CP;
+          // 128-column slot index within the row: 2 * NB slots, tile nb covers BNT / 128 of them
+          float* dst = p.part + (grow * (size_t)(2 * p.NB) + nb * (BNT / 128) + slot) * CP;
 #pragma unroll
           for (int c = 0; c < CP; ++c) dst[c] = eacc[c];
         }
@@ -670,7 +676,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
         if (CTAS == 2) mbar_arrive_cluster(mapa_rank(eb, 0));
         else mbar_arrive(eb);
       }
-      if (LAYER == 3 && CP <= 8) {
+      if (kCanFuse) {
         if (p.fuse) {
           // publish: my partials are visible GPU-wide (fence) for all 128 rows (barrier) before the row group is
           // signalled; then tell this CTA's helper warps that job `it` exists
@@ -689,10 +695,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
     // Job j = scheduled tile j of this CTA.  It can run once (a) this CTA's epilogue has published tile j and (b) all
     // NB column tiles of the row group have arrived.  Arrivals never wait for a helper, so the blocking waits below
     // cannot dead-lock, whatever the order in which CTAs become resident.
-    if (LAYER == 3 && CP <= 8) {
+    if (kCanFuse) {
       if (p.fuse) {
         const int ht = threadIdx.x - kHelperWarp0 * 32;   // 0..127
-        float* sYn = sEpi + BN * (2 + CP);
+        float* sYn = sEpi + BNT * (2 + CP);
         for (int job = 0;; ++job) {
           const int32_t code = __ldg(my_sched + job);
           if (code < 0) break;
@@ -926,9 +932,9 @@ bool make_tmap(ladine_handle* h, CUtensorMap* out, const void* base, uint64_t ro
 
 // instruction descriptor for kind::f16 (PTX ISA "Instruction descriptor"): D format F32 (1) at [4,6);
 // A/B format (0 = F16, 1 = BF16) at [7,10)/[10,13); A,B K-major (0) at 15/16; N>>3 at [17,23); M>>4 at [24,29)
-uint32_t make_idesc(bool bf16, int ctas) {
+uint32_t make_idesc(bool bf16, int ctas, int n = BN) {
   const uint32_t fmt = bf16 ? 1u : 0u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * ctas) >> 4) << 24);
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)((BM * ctas) >> 4) << 24);
 }
 
 // Programmatic dependent launch is OPT-IN (ladine_set_option("pdl", 1)) and only ever applied to chains of
@@ -937,10 +943,10 @@ uint32_t make_idesc(bool bf16, int ctas) {
 // steps of a 1000-step chain (driver 580.159) -- so a chain that uses pairs never sets the attribute.
 inline bool pdl_allowed(const ladine_handle* h, int ctas) { return h->pdl && ctas == 1; }
 
-template <int LAYER, typename T16, int CP, int CTAS>
+template <int LAYER, typename T16, int CP, int CTAS, int BNT = BN>
 cudaError_t launch_gemm_t(const GemmParams& p, int grid, bool pdl, cudaStream_t st) {
   const size_t smem = tensor_gemm_smem_bytes(CP);
-  auto kern = trunk_gemm_kernel<LAYER, T16, CP, CTAS>;
+  auto kern = trunk_gemm_kernel<LAYER, T16, CP, CTAS, BNT>;
   // cheap (host-side table update); done per launch so it is right for every device of the process
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -966,13 +972,18 @@ cudaError_t launch_gemm_t(const GemmParams& p, int grid, bool pdl, cudaStream_t 
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
+// ctas: 1 = single-CTA 128 x 256 tiles, 2 = CTA pairs, kGeomSlim = single-CTA 128 x 128 tiles
+constexpr int kGeomSlim = 3;
+
 template <int LAYER, typename T16>
 cudaError_t launch_gemm_c(const GemmParams& p, int grid, int Cp, int ctas, bool pdl, cudaStream_t st) {
   if (LAYER == 2) {  // the layer-2 epilogue does not depend on the class count
+    if (ctas == kGeomSlim) return launch_gemm_t<2, T16, 2, 1, 128>(p, grid, pdl, st);
     return ctas == 2 ? launch_gemm_t<2, T16, 2, 2>(p, grid, pdl, st) : launch_gemm_t<2, T16, 2, 1>(p, grid, pdl, st);
   }
 #define LADINE_GEMM_CASE(CPV)                                                                          \
   case CPV:                                                                                            \
+    if (ctas == kGeomSlim) return launch_gemm_t<3, T16, CPV, 1, 128>(p, grid, pdl, st);                \
     return ctas == 2 ? launch_gemm_t<3, T16, CPV, 2>(p, grid, pdl, st) : launch_gemm_t<3, T16, CPV, 1>(p, grid, pdl, st);
   switch (Cp) {
     LADINE_GEMM_CASE(2)
@@ -1079,8 +1090,9 @@ struct ProfSpan {
 }  // namespace
 
 size_t tensor_gemm_smem_bytes(int Cp) {
-  static_assert(GemmCfg<1>::kStages * GemmCfg<1>::kStageBytes == GemmCfg<2>::kStages * GemmCfg<2>::kStageBytes,
-                "both pipeline geometries use the same ring size");
+  static_assert(GemmCfg<1>::kStages * GemmCfg<1>::kStageBytes == GemmCfg<2>::kStages * GemmCfg<2>::kStageBytes &&
+                    GemmCfg<1>::kStages * GemmCfg<1>::kStageBytes == GemmCfg<1, 128>::kStages * GemmCfg<1, 128>::kStageBytes,
+                "all pipeline geometries use the same ring size");
   return 1024 /*alignment slack*/ + (size_t)GemmCfg<1>::kStages * GemmCfg<1>::kStageBytes +
          sizeof(float) * (BN * (2 + Cp) + BM * Cp) + sizeof(GemmBarriers);
 }
@@ -1162,7 +1174,12 @@ size_t sched_bytes_bound(int K, int rows, int NB) {
   return (items + 148 * 4) * sizeof(int32_t) * 2;
 }
 
-int choose_ctas(const ladine_handle* h, int rows) {
+int choose_ctas(const ladine_handle* h, int K, int rows, int Fp) {
+  // slim 128 x 128 tiles: forced ("ctas" = 3) or, on auto, when even twice as many tiles still fit the SMs in one
+  // round (measured at one member x 64 rows: 31.2 -> 27.5 us per layer; with 80 wide tiles -- two rounds of slim
+  // ones -- 45.6 -> 54.9 us, hence the one-round condition)
+  const long long wide_tiles = (long long)K * ((rows + BM - 1) / BM) * (Fp / BN);
+  if (h->ctas == kGeomSlim || (h->ctas == 0 && 2 * wide_tiles <= (long long)h->sm_count)) return kGeomSlim;
   if (h->ctas == 1 || h->ctas == 2) return h->ctas;
   // cost in single-CTA 128-row tile times; a full pair tile (256 rows on 2 SMs) costs 2 / pair_gain, a half
   // tile 1.7 / pair_gain (see plan_tiles).  Pairs must win by 3 % to be chosen (static-schedule quantisation).
@@ -1211,12 +1228,15 @@ struct TensorChain {
     Cp = m0->Cp;
     K = a.K;
     const int rows = a.N * a.D;
-    ctas = choose_ctas(h, rows);
-    pdl = pdl_allowed(h, ctas);
+    ctas = choose_ctas(h, K, rows, Fp);
+    const bool slim = ctas == kGeomSlim;
+    const int cpu = slim ? 1 : ctas;            // CTAs per scheduling unit (2 for pairs)
+    const int bnt = slim ? 128 : BN;            // tile width
+    pdl = pdl_allowed(h, cpu) && !slim;
     // the fused tail + head spins on other CTAs of the same launch: every CTA must be resident, so it is only
     // used when this chain is the sole lane, and its extra per-column parameters fit in smem up to 8 classes
-    fuse = h->fuse && single_lane && Cp <= 8;
-    const int NBt = Fp / BN;
+    fuse = h->fuse && single_lane && Cp <= 8 && !slim;
+    const int NBt = Fp / bnt;                   // column tiles per row tile
     if ((rows + BM - 1) / BM > 4096 || NBt > 1024) {
       *err = "too many rows per member for one launch group (max 524288 chains): tile the images (NestedEnsemble does)";
       return cudaErrorInvalidValue;
@@ -1227,8 +1247,8 @@ struct TensorChain {
     // the activations are read once and the member's 32 MiB W cycles through L2.  "order" option: 0 auto, 1 / 2 force.
     const size_t act_bytes = (size_t)((rows + BM - 1) / BM) * BM * Fp * 2;
     const bool row_major = h->order == 2 || (h->order == 0 && act_bytes > kRowMajorActBytes);
-    const TilePlan plan = plan_tiles(K, rows, NBt, ctas, h->sm_count / ctas, row_major);
-    const TilePlan plan3 = (fuse && !row_major) ? plan_tiles(K, rows, NBt, ctas, h->sm_count / ctas, /*row_major=*/true) : plan;
+    const TilePlan plan = plan_tiles(K, rows, NBt, cpu, h->sm_count / cpu, row_major);
+    const TilePlan plan3 = (fuse && !row_major) ? plan_tiles(K, rows, NBt, cpu, h->sm_count / cpu, /*row_major=*/true) : plan;
     const int rows_pad = plan.rows_pad;
     const size_t m_total = (size_t)K * rows_pad;
     const size_t sched_half = sched_bytes_bound(K, rows, NBt) / (2 * sizeof(int32_t));  // ints per table
@@ -1241,24 +1261,24 @@ struct TensorChain {
       e = cudaMemcpyAsync(sched3, plan3.table.data(), plan3.table.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st);
     const int mblk_total = plan.n_full + plan.has_half;
     if (e == cudaSuccess && fuse)
-      e = cudaMemsetAsync(ws.arrivals, 0, sizeof(int) * (size_t)K * mblk_total * ctas, st);
+      e = cudaMemsetAsync(ws.arrivals, 0, sizeof(int) * (size_t)K * mblk_total * cpu, st);
     if (e != cudaSuccess) return e;
     if (!make_tmap(h, &g2.tmA, ws.h1, m_total, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
     if (!make_tmap(h, &g3.tmA, ws.h2, m_total, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
     for (int k = 0; k < K; ++k) {
-      if (!make_tmap(h, &g2.tmB[k], members[k]->W2h, Fp, Fp, BN / ctas, bf16, err)) return cudaErrorInvalidValue;
-      if (!make_tmap(h, &g3.tmB[k], members[k]->W3h, Fp, Fp, BN / ctas, bf16, err)) return cudaErrorInvalidValue;
+      if (!make_tmap(h, &g2.tmB[k], members[k]->W2h, Fp, Fp, bnt / cpu, bf16, err)) return cudaErrorInvalidValue;
+      if (!make_tmap(h, &g3.tmB[k], members[k]->W3h, Fp, Fp, bnt / cpu, bf16, err)) return cudaErrorInvalidValue;
       g3.W4[k] = members[k]->W4;
     }
     for (GemmParams* g : {&g2, &g3}) {
       g->Fp = Fp;
-      g->NB = NBt;
+      g->NB = Fp / BN;   // 256-column groups: the lin4 partial buffer has 2 * NB slots per row whatever the tile width
       g->KB = Fp / BK;
       g->rows = rows;
       g->rows_pad = rows_pad;
       g->sched = ws.sched;
       g->sched_stride = plan.stride;
-      g->idesc = make_idesc(bf16, ctas);
+      g->idesc = make_idesc(bf16, cpu, bnt);
       g->idesc_half = make_idesc(bf16, 1);  // M = 128 across the pair
       g->fuse = 0;
     }
@@ -1269,7 +1289,7 @@ struct TensorChain {
     g3.group_arrivals = ws.arrivals;
     g2.h_out = ws.h2;
     g3.part = ws.part;
-    grid = plan.units * ctas;
+    grid = plan.units * cpu;
 
     for (int k = 0; k < K; ++k) {
       tp.W1y[k] = members[k]->W1y;
@@ -1406,13 +1426,16 @@ cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int lay
   cudaError_t e = resolve_encode(h, err);
   if (e != cudaSuccess) return e;
   const int Fp = m->Fp;
-  const int ctas = (h->ctas == 2) ? 2 : 1;  // debug entry: "ctas" = 2 exercises the CTA-pair geometry (incl. half tiles)
-  const TilePlan plan = plan_tiles(1, rows, Fp / BN, ctas, h->sm_count / ctas);
+  // debug entry: "ctas" = 2 exercises the CTA-pair geometry (incl. half tiles), 3 the slim 128-wide tiles
+  const bool slim = h->ctas == kGeomSlim;
+  const int ctas = (h->ctas == 2) ? 2 : 1;
+  const int bnt = slim ? 128 : BN;
+  const TilePlan plan = plan_tiles(1, rows, Fp / bnt, ctas, h->sm_count / ctas);
   e = cudaMemcpyAsync(sched_buf, plan.table.data(), plan.table.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return e;
   GemmParams g{};
   if (!make_tmap(h, &g.tmA, h_in, (uint64_t)plan.rows_pad, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
-  if (!make_tmap(h, &g.tmB[0], layer == 2 ? m->W2h : m->W3h, Fp, Fp, BN / ctas, bf16, err)) return cudaErrorInvalidValue;
+  if (!make_tmap(h, &g.tmB[0], layer == 2 ? m->W2h : m->W3h, Fp, Fp, bnt / ctas, bf16, err)) return cudaErrorInvalidValue;
   g.scale[0] = m->A[layer - 1] + (size_t)t * Fp;
   g.shift[0] = m->Cc[layer - 1] + (size_t)t * Fp;
   g.W4[0] = m->W4;
@@ -1425,11 +1448,12 @@ cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int lay
   g.rows_pad = plan.rows_pad;
   g.sched = sched_buf;
   g.sched_stride = plan.stride;
-  g.idesc = make_idesc(bf16, ctas);
+  g.idesc = make_idesc(bf16, ctas, bnt);
   g.idesc_half = make_idesc(bf16, 1);
   const int grid = plan.units * ctas;
-  return layer == 2 ? launch_gemm<2>(g, grid, bf16, m->Cp, ctas, false, st)
-                    : launch_gemm<3>(g, grid, bf16, m->Cp, ctas, false, st);
+  const int geom = slim ? kGeomSlim : ctas;
+  return layer == 2 ? launch_gemm<2>(g, grid, bf16, m->Cp, geom, false, st)
+                    : launch_gemm<3>(g, grid, bf16, m->Cp, geom, false, st);
 }
 
 }  // namespace ladine

@@ -104,12 +104,12 @@ def pair_mode():
     engine.set_option(0, "ctas", 0)
 
 
-@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("ctas", [1, 2, 3])
 @pytest.mark.parametrize("F,rows,prec", [(256, 128, "fp16"), (256, 100, "bf16"), (512, 300, "fp16"), (1024, 257, "fp16"),
                                          (512, 640, "fp16"), (256, 1400, "fp16")])
 def test_single_gemm_layer(F, rows, prec, ctas):
     """ladine_debug_layer: one tcgen05 GEMM + fused epilogue vs torch FP64 on identically rounded operands,
-    for both tile geometries (cta_group::1 128x256 tiles, cta_group::2 256x256 pair tiles)."""
+    for every tile geometry (cta_group::1 128x256 tiles, cta_group::2 256x256 pair tiles, slim 128x128 tiles)."""
     from nested_diffusion_b200 import engine
 
     engine.set_option(0, "ctas", ctas)
@@ -165,7 +165,7 @@ def test_pair_mode_chain_matches_reference_golden(name, pair_mode):
 
 
 def test_pair_mode_equals_single_mode_bitwise():
-    """Tile geometry (single CTA / CTA pair + half tiles), tile order (N-tile-major / row-major), lane count and the
+    """Tile geometry (single CTA / CTA pair + half tiles / slim 128-wide tiles), tile order (N-tile-major / row-major), lane count and the
     fused tail+head epilogue all compute every chain with the same arithmetic in the same order -> identical bits (incl. trajectory, probs)."""
     import nested_diffusion_b200 as nd
     from nested_diffusion_b200 import engine
@@ -181,7 +181,7 @@ def test_pair_mode_equals_single_mode_bitwise():
     coef = coef_table(alphas, omabs, T)
     outs = {}
     for ctas, lanes, fuse, order in ((1, 1, 0, 1), (1, 1, 1, 0), (2, 1, 1, 0), (2, 1, 0, 1), (1, 2, 1, 0), (2, 3, 1, 0),
-                                     (1, 1, 0, 2), (2, 1, 0, 2), (1, 2, 1, 2)):
+                                     (1, 1, 0, 2), (2, 1, 0, 2), (1, 2, 1, 2), (3, 1, 0, 1), (3, 2, 1, 2), (0, 1, 0, 0)):
         engine.set_option(0, "ctas", ctas)
         engine.set_option(0, "lanes", lanes)
         engine.set_option(0, "fuse", fuse)
