@@ -16,7 +16,7 @@ h_out = torch.zeros(rows_pad, pm.Fp, dtype=torch.float16, device="cuda")
 part = torch.zeros(rows_pad, pm.Fp // 256, 2, pm.Cp, device="cuda")
 lib, h = _capi.load(), _capi.handle(0)
 st = torch.cuda.current_stream().cuda_stream
-for ctas in (1, 2):
+for ctas in (1, 2, 3):
     engine.set_option(0, "ctas", ctas)
     for layer in (2, 3):
         for _ in range(5):
