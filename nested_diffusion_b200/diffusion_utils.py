@@ -66,7 +66,7 @@ def _prepare(model, x, y_0_hat, y_T_mean, output_detach, precision):
             raise ValueError(f"{name} is on {t.device} but the model is on {device}")
     if y_0_hat.dim() != 2 or y_0_hat.shape != y_T_mean.shape or y_0_hat.shape[0] != x.shape[0]:
         raise ValueError("expected x [B, ...], y_0_hat [B, C], y_T_mean [B, C]")
-    xf = engine.encode_features(model, x).unsqueeze(0)
+    xf = engine.features_of(model, x).unsqueeze(0)   # once per (model, image tensor): see engine.features_of
     return pm, xf, y_0_hat.unsqueeze(0), y_T_mean.unsqueeze(0)
 
 

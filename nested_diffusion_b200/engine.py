@@ -193,6 +193,32 @@ def encode_features(model, x: torch.Tensor, mode: str = "fp32") -> torch.Tensor:
         return model.norm(model.encoder_x(x))
 
 
+_XF_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _encoder_fingerprint(model) -> tuple:
+    sd = model.state_dict(keep_vars=True)
+    return tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in sd.items()
+                 if not k.startswith(("lin", "unetnorm")))
+
+
+def features_of(model, x: torch.Tensor) -> torch.Tensor:
+    """``encode_features(model, x)``, remembered for the LAST ``x`` of each model.
+
+    The reference's runner calls ``p_sample_loop`` 20 times per member with the very same image tensor
+    (classification_train_separately.py:770-777) and re-evaluates the 2.4 GB encoder layer inside every one of the
+    T steps of every call; the drop-in evaluates it once per call, and with this cache once per (member, batch).
+    A hit needs the same tensor OBJECT (a strong reference is kept, so its address cannot be recycled), an unchanged
+    in-place version counter, and unchanged encoder / norm parameters; the returned features are read-only."""
+    key = (_encoder_fingerprint(model), x._version, tuple(x.shape), x.dtype, bool(getattr(model, "training", False)))
+    hit = _XF_CACHE.get(model)
+    if hit is not None and hit[0] is x and hit[1] == key:
+        return hit[2]
+    xf = encode_features(model, x)
+    _XF_CACHE[model] = (x, key, xf)
+    return xf
+
+
 def fresh_seed() -> int:
     """A Philox key drawn from torch's default CPU generator, so ``torch.manual_seed`` makes runs repeatable."""
     return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())

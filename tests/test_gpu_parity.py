@@ -350,6 +350,42 @@ def test_error_behaviour():
         du.p_sample_loop(model, x.cuda(), yhat.cuda()[:3], yhat.cuda(), m["T"], alphas, omabs)
 
 
+def test_encoder_features_are_remembered_per_image_tensor_only():
+    """p_sample_loop keeps norm(encoder_x(x)) of the last image tensor of a model (the runner passes the same tensor
+    for all 20 draws of a member); an in-place change of x or of an encoder parameter must invalidate it."""
+    from nested_diffusion_b200 import diffusion_utils as du
+    from nested_diffusion_b200 import engine
+
+    fx = ChainFixture("small_f128_t50")
+    m = fx.meta
+    sd, x, yhat, noise, alphas, omabs = fx.materialize()
+    model = make_model(m, sd)
+    xc, yc, nc = x.cuda(), yhat.cuda(), noise.cuda()
+
+    def run(xx):
+        with torch.no_grad():
+            return du.p_sample_loop(model, xx, yc, yc, m["T"], alphas, omabs, only_last_sample=True, noise=nc)
+
+    first = run(xc)
+    f1 = engine.features_of(model, xc)
+    assert engine.features_of(model, xc) is f1, "same tensor object, unchanged: cached"
+    assert torch.equal(run(xc), first)
+    assert rel_err(first.cpu(), fx["y0"]) <= TOL["fp32"]
+    twin = xc.clone()
+    assert engine.features_of(model, twin) is not f1, "equal values in another tensor object: recomputed"
+    assert torch.equal(run(twin), first)
+    xc.mul_(0.5)                                   # in-place edit bumps the version counter
+    changed = run(xc)
+    assert not torch.equal(changed, first)
+    with torch.no_grad():
+        want = du.p_sample_loop(model, xc.clone(), yc, yc, m["T"], alphas, omabs, only_last_sample=True, noise=nc)
+    assert torch.equal(changed, want)
+    f2 = engine.features_of(model, xc)
+    with torch.no_grad():
+        model.norm.bias.add_(0.25)                  # an encoder-side parameter changes
+    assert engine.features_of(model, xc) is not f2
+
+
 def test_empty_and_single_row_batches():
     """Edge shapes of the drop-in: an empty batch is a valid call (the reference's ops are no-ops on [0, C]) and a
     single row must equal the same row sampled inside a larger batch on the same injected noise."""
