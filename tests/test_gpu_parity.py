@@ -201,6 +201,74 @@ def test_pair_mode_equals_single_mode_bitwise():
             assert torch.equal(ref[name], val[name]), (key, name)
 
 
+@pytest.mark.slow
+def test_config2_full_width_properties():
+    """BASELINE config 2 at its full width and row count (K=5 members x 70 images x 20 draws, F=4096; 12 reverse
+    steps keep it fast) through properties that need no reference run: run-to-run bitwise determinism, bitwise
+    independence of the tile geometry and order, bitwise invariance under image sharding and under draw sharding
+    (global Philox ids), member-subset consistency, finite outputs and probabilities that sum to one."""
+    import nested_diffusion_b200 as nd
+    from nested_diffusion_b200 import engine
+    from nested_diffusion_b200.schedule import coef_table
+
+    K, N, D, F, Cc, T = 5, 70, 20, 4096, 2, 12
+    dev = torch.device("cuda")
+
+    def member(seed):
+        gg = torch.Generator(device="cuda").manual_seed(seed)
+        r = lambda *sh: torch.rand(*sh, device=dev, generator=gg)
+        sd = {}
+        for l, i in ((1, 2 * Cc), (2, F), (3, F)):
+            b = 1 / i ** 0.5
+            sd[f"lin{l}.lin.weight"] = (r(F, i) * 2 - 1) * b
+            sd[f"lin{l}.lin.bias"] = (r(F) * 2 - 1) * b
+            sd[f"lin{l}.embed.weight"] = r(T + 1, F)
+            sd[f"unetnorm{l}.weight"] = r(F) + 0.5
+            sd[f"unetnorm{l}.bias"] = torch.randn(F, device=dev, generator=gg) * 0.2
+            sd[f"unetnorm{l}.running_mean"] = torch.randn(F, device=dev, generator=gg) * 0.3
+            sd[f"unetnorm{l}.running_var"] = r(F) + 0.5
+        sd["lin4.weight"] = (r(Cc, F) * 2 - 1) / F ** 0.5
+        sd["lin4.bias"] = (r(Cc) * 2 - 1) / F ** 0.5
+        return sd
+
+    pms = [nd.PackedMember(member(900 + k), n_steps=T, precision="fp16") for k in range(K)]
+    g = torch.Generator(device="cuda").manual_seed(2)
+    xf = torch.randn(K, N, F, device=dev, generator=g)
+    yh = torch.softmax(torch.randn(K, N, Cc, device=dev, generator=g), -1)
+    alphas, omabs = orc.schedule_tensors(orc.make_beta_schedule("linear", T, 1e-4, 0.02))
+    coef = coef_table(alphas, omabs, T)
+    ids = list(range(K))
+
+    def run(**kw):
+        return engine.sample_chains(pms, xf, yh, yh, coef, D, seed=41, member_ids=ids, temperature=0.1737, **kw)
+
+    ref = run()
+    assert torch.isfinite(ref["y"]).all() and tuple(ref["y"].shape) == (K, D, N, Cc)
+    assert torch.allclose(ref["probs"].sum(-1), torch.ones(K, D, N, device=dev), atol=1e-5)
+    assert torch.equal(run()["y"], ref["y"]), "run-to-run determinism"
+    for opt, val in (("ctas", 2), ("order", 2), ("lanes", 2), ("tail_vec", 8)):
+        engine.set_option(0, opt, val)
+        try:
+            alt = run()
+        finally:
+            engine.set_option(0, opt, 1 if opt == "lanes" else 0)
+        assert torch.equal(alt["y"], ref["y"]) and torch.equal(alt["probs"], ref["probs"]), opt
+    # image shards (what each rank of a multi-GPU run computes)
+    parts = []
+    for r in range(3):
+        lo, hi = nd.shard_bounds(N, r, 3)
+        parts.append(engine.sample_chains(pms, xf[:, lo:hi], yh[:, lo:hi], yh[:, lo:hi], coef, D, seed=41, member_ids=ids,
+                                          image_offset=lo, images_total=N)["y"])
+    assert torch.equal(torch.cat(parts, dim=2), ref["y"]), "image sharding"
+    # draw shards
+    halves = [engine.sample_chains(pms, xf, yh, yh, coef, D // 2, seed=41, member_ids=ids, draw_offset=o,
+                                   draws_total=D)["y"] for o in (0, D // 2)]
+    assert torch.equal(torch.cat(halves, dim=1), ref["y"]), "draw sharding"
+    # a member subset reproduces its own chains
+    sub = engine.sample_chains(pms[3:], xf[3:], yh[3:], yh[3:], coef, D, seed=41, member_ids=ids[3:])["y"]
+    assert torch.equal(sub, ref["y"][3:]), "member subset"
+
+
 def test_philox_equals_injected_replay_and_is_deterministic():
     """Philox stream == ladine_fill_noise replay (bitwise), run-to-run bitwise reproducible."""
     import nested_diffusion_b200 as nd
