@@ -22,11 +22,24 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found")
 
 
+STAMP = OUT + ".srchash"   # travels with the .so; file times do not survive a snapshot copy, contents do
+
+
+def source_hash() -> str:
+    import hashlib
+
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    for p in SRC + HDR:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def up_to_date() -> bool:
-    if not os.path.exists(OUT):
+    if not (os.path.exists(OUT) and os.path.exists(STAMP)):
         return False
-    t = os.path.getmtime(OUT)
-    return all(os.path.getmtime(p) <= t for p in SRC + HDR)
+    with open(STAMP) as f:
+        return f.read().strip() == source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -40,6 +53,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libladine.so")
     if verbose:
         sys.stderr.write(r.stderr)
+    with open(STAMP, "w") as f:
+        f.write(source_hash() + "\n")
     return OUT
 
 

@@ -42,6 +42,20 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(_capi.SampleArgs) % 8 == 0
 
 
+def test_build_freshness_is_content_based(monkeypatch):
+    """The in-tree library is rebuilt when the sources or flags change, not when file times do (a snapshot copy to the
+    GPU box does not preserve mtimes)."""
+    from nested_diffusion_b200 import build as b
+
+    b.build()
+    assert b.up_to_date()
+    h0 = b.source_hash()
+    os.utime(b.SRC[0], None)                      # touching a source changes nothing
+    assert b.up_to_date() and b.source_hash() == h0
+    monkeypatch.setattr(b, "FLAGS", b.FLAGS + ["-DX"])
+    assert not b.up_to_date()
+
+
 def test_create_fails_cleanly_without_a_device():
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
