@@ -122,6 +122,18 @@ def test_drop_in_module_surface():
 
 
 # ------------------------------------------------------------------ schedules / coefficients
+def test_module_swap_shims_bind_the_drop_in():
+    """shims/ ahead of the reference on sys.path: the runner's own import lines resolve to this package."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from diffusion_utils import *\n"
+            "from latent_model import ConditionalModel\n"
+            "import nested_diffusion_b200.diffusion_utils as du, nested_diffusion_b200.latent_model as lm\n"
+            "assert p_sample_loop is du.p_sample_loop and p_sample is du.p_sample and make_beta_schedule is du.make_beta_schedule\n"
+            "assert ConditionalModel is lm.ConditionalModel\n" % (ROOT, os.path.join(ROOT, "shims")))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
 def test_schedules_and_coef_table_equal_oracle_bitwise():
     fx = Fixture("schedules")
     for key, ref in fx.arrays.items():
