@@ -177,6 +177,16 @@ int ladine_get_profile(ladine_handle* h, float ms_out[4], int64_t count_out[3]);
  * Uses (and may grow) the handle's workspace: do not overlap with an in-flight ladine_sample on the handle. */
 int ladine_debug_layer(ladine_handle* h, const ladine_member* member, int layer, int t, const void* h_in,
                        int rows, void* h_out, float* part, void* stream);
+/* Debug/test entry, host only (needs no device or handle): the static tile schedule a GEMM launch would use.
+ *   geometry : 1 = 128x256 single-CTA tiles, 2 = CTA pairs (256x256 + 2x64-row half tiles), 3 = slim 128x128 tiles
+ *   row_major: 0 = (member, N tile, row tile) order, 1 = (member, row tile, N tile)
+ *   units    : scheduling units available (SMs, or SM pairs for geometry 2)
+ * Writes up to `cap` int32 entries -- units_used rows of `stride` entries, each row the tiles of one unit in order,
+ * terminated/padded with -1; entry = member << 23 | n_tile << 13 | row_tile << 1 | half -- and returns the number
+ * of entries the table holds (> cap: nothing written), or a negative ladine_status.
+ * info_out[4] = {units_used, stride, rows_pad, row tiles per member}. */
+int64_t ladine_debug_plan(int32_t K, int32_t rows, int32_t feature_dim_padded, int32_t geometry, int32_t row_major,
+                          int32_t units, int32_t* table_out, int64_t cap, int32_t info_out[4]);
 /* padded feature dim and padded class count used by the packed layout */
 int ladine_member_fpad(const ladine_member* m);
 int ladine_member_cpad(const ladine_member* m);

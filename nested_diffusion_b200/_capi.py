@@ -61,6 +61,8 @@ SYMBOLS = {
     "ladine_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "ladine_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "ladine_get_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
+    "ladine_debug_plan": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int32)]),
     "ladine_debug_layer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
 }

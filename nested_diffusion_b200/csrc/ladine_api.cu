@@ -676,6 +676,14 @@ int ladine_get_profile(ladine_handle* h, float ms_out[4], int64_t count_out[3]) 
   return LADINE_OK;
 }
 
+int64_t ladine_debug_plan(int32_t K, int32_t rows, int32_t feature_dim_padded, int32_t geometry, int32_t row_major,
+                          int32_t units, int32_t* table_out, int64_t cap, int32_t info_out[4]) {
+  if (K < 1 || K > LADINE_MAX_GROUP || rows < 1 || feature_dim_padded < 256 || feature_dim_padded % 256 != 0 ||
+      geometry < 1 || geometry > 3 || units < 1 || !info_out || (rows + 127) / 128 > 4096)
+    return LADINE_ERR_INVALID;
+  return ladine::debug_plan(K, rows, feature_dim_padded, geometry, row_major, units, table_out, cap, info_out);
+}
+
 int ladine_debug_layer(ladine_handle* h, const ladine_member* member, int layer, int t, const void* h_in, int rows,
                        void* h_out, float* part, void* stream) {
   if (!h) return LADINE_ERR_INVALID;

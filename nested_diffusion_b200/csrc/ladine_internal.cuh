@@ -96,6 +96,8 @@ void tensor_chain_destroy(TensorChain* c);
 cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int layer, int t, const void* h_in, int rows,
                                void* h_out, float* part, int32_t* sched_buf, cudaStream_t st, std::string* err);
 size_t sched_bytes_bound(int K, int rows, int NB);
+int64_t debug_plan(int K, int rows, int Fp, int geometry, int row_major, int units, int32_t* table_out, int64_t cap,
+                   int32_t info_out[4]);
 size_t tensor_gemm_smem_bytes(int Cp);
 
 // ---- shared small kernels (ladine_api.cu) ----

@@ -1420,6 +1420,20 @@ TensorChain* tensor_chain_create(ladine_handle* h, const ladine_member* const* m
 cudaError_t tensor_chain_step(TensorChain* c, int t, int64_t* launches) { return c->step(t, launches); }
 void tensor_chain_destroy(TensorChain* c) { delete c; }
 
+int64_t debug_plan(int K, int rows, int Fp, int geometry, int row_major, int units, int32_t* table_out, int64_t cap,
+                   int32_t info_out[4]) {
+  const int cpu = geometry == 2 ? 2 : 1;
+  const int bnt = geometry == kGeomSlim ? 128 : BN;
+  const TilePlan plan = plan_tiles(K, rows, Fp / bnt, cpu, units, row_major != 0);
+  info_out[0] = plan.units;
+  info_out[1] = plan.stride;
+  info_out[2] = plan.rows_pad;
+  info_out[3] = plan.n_full + plan.has_half;
+  const int64_t n = (int64_t)plan.table.size();
+  if (n <= cap && table_out) std::copy(plan.table.begin(), plan.table.end(), table_out);
+  return n;
+}
+
 cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int layer, int t, const void* h_in, int rows,
                                void* h_out, float* part, int32_t* sched_buf, cudaStream_t st, std::string* err) {
   const bool bf16 = m->precision == LADINE_PREC_BF16;

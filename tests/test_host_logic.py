@@ -56,6 +56,74 @@ def test_build_freshness_is_content_based(monkeypatch):
     assert not b.up_to_date()
 
 
+def _plan(K, rows, Fp, geometry, row_major, units):
+    lib = _capi.load()
+    info = (ctypes.c_int32 * 4)()
+    n = lib.ladine_debug_plan(K, rows, Fp, geometry, row_major, units, None, 0, info)
+    assert n > 0
+    buf = (ctypes.c_int32 * n)()
+    assert lib.ladine_debug_plan(K, rows, Fp, geometry, row_major, units, buf, n, info) == n
+    used, stride, rows_pad, row_tiles = list(info)
+    table = np.frombuffer(buf, dtype=np.int32).reshape(used, stride)
+    return table, rows_pad, row_tiles
+
+
+@pytest.mark.parametrize("K,rows,Fp,geometry,units", [
+    (5, 1400, 4096, 1, 148),     # config 2, single-CTA tiles
+    (5, 1400, 4096, 2, 74),      # config 2 as CTA pairs: 5 full pair tiles + one half tile per (member, N tile)
+    (1, 64, 4096, 3, 148),       # config 1, slim tiles
+    (5, 20480, 4096, 2, 74),     # config 3
+    (3, 300, 512, 1, 148), (2, 257, 1024, 2, 74), (8, 1, 256, 1, 148), (1, 129, 768, 3, 7),
+])
+@pytest.mark.parametrize("row_major", [0, 1])
+def test_static_tile_schedule_covers_every_tile_once_and_balances(K, rows, Fp, geometry, units, row_major):
+    """ladine_debug_plan (host-only): the schedule every GEMM launch reads.  Every (member, N tile, row tile) appears
+    exactly once, rows terminate with -1, half tiles only where a pair geometry has <= 128 trailing rows, and the
+    per-unit load is balanced to within one tile."""
+    table, rows_pad, row_tiles = _plan(K, rows, Fp, geometry, row_major, units)
+    tile_cols = 128 if geometry == 3 else 256
+    tile_rows = 256 if geometry == 2 else 128
+    NB = Fp // tile_cols
+    rem = rows % tile_rows
+    has_half = geometry == 2 and 0 < rem <= 128
+    assert row_tiles == (rows // tile_rows) + (1 if rem else 0)
+    assert rows_pad == row_tiles * tile_rows and rows_pad >= rows
+    seen, loads, order = set(), [], []
+    for unit in table:
+        live = unit[unit >= 0]
+        assert (unit[len(live):] == -1).all() and len(live) < len(unit), "tiles first, then the -1 terminator"
+        cost = 0
+        for code in live:
+            member, nb, mb, half = int(code) >> 23, (int(code) >> 13) & 1023, (int(code) >> 1) & 4095, int(code) & 1
+            assert 0 <= member < K and 0 <= nb < NB and 0 <= mb < row_tiles
+            assert half == (1 if has_half and mb == row_tiles - 1 else 0)
+            assert (member, nb, mb) not in seen
+            seen.add((member, nb, mb))
+            order.append((member, nb, mb))
+            cost += 17 if half else 20
+        loads.append(cost)
+    assert len(seen) == K * NB * row_tiles
+    assert len(table) == min(units, K * NB * row_tiles)
+    assert max(loads) - min(loads) <= 20, "longest-processing-time quotas: no unit is more than one tile ahead"
+    # neighbours in the canonical order run at the same time: the first tile of every unit belongs to one member and,
+    # in N-tile-major order, to as few N tiles as possible (they share the W tile)
+    first = [(int(u[0]) >> 23, (int(u[0]) >> 13) & 1023, (int(u[0]) >> 1) & 4095) for u in table]
+    if len(table) <= NB * row_tiles:
+        assert len({f[0] for f in first}) == 1
+        if row_major:
+            assert len({f[2] for f in first}) <= -(-len(table) // NB) + 1
+        else:
+            assert len({f[1] for f in first}) <= -(-len(table) // row_tiles) + 1
+
+
+def test_debug_plan_rejects_bad_arguments():
+    lib = _capi.load()
+    info = (ctypes.c_int32 * 4)()
+    for args in ((0, 10, 256, 1, 0, 8), (1, 0, 256, 1, 0, 8), (1, 10, 300, 1, 0, 8), (1, 10, 256, 4, 0, 8),
+                 (1, 10, 256, 1, 0, 0), (9, 10, 256, 1, 0, 8)):
+        assert lib.ladine_debug_plan(*args, None, 0, info) < 0
+
+
 def test_create_fails_cleanly_without_a_device():
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
