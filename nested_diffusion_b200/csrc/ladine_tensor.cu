@@ -17,6 +17,9 @@
 //   warp 8      TMA producer   (cp.async.bulk.tensor 2D, 128B swizzle, mbarrier ring)
 //   warp 9      MMA issuer     (tcgen05.mma kind::f16, cta_group::1 M=128 / cta_group::2 M=256, N=256 K=16, one thread)
 //   TMEM: 2 accumulator stages x 256 columns so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Tile geometries (all bit-identical, chosen per call by choose_ctas): 128 x 256 single-CTA tiles, 256 x 256 CTA-pair
+// tiles (+ 2 x 64-row half tiles), slim 128 x 128 single-CTA tiles for calls too small to fill the SMs.  Tile order
+// (plan_tiles): N-tile-major while a member's activations fit in L2, row-major beyond.
 #include <cstdio>
 
 #include "ladine_internal.cuh"
