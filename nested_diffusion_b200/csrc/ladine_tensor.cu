@@ -1235,7 +1235,7 @@ struct TensorChain {
     const bool slim = ctas == kGeomSlim;
     const int cpu = slim ? 1 : ctas;            // CTAs per scheduling unit (2 for pairs)
     const int bnt = slim ? 128 : BN;            // tile width
-    pdl = pdl_allowed(h, cpu) && !slim;
+    pdl = pdl_allowed(h, cpu);
     // the fused tail + head spins on other CTAs of the same launch: every CTA must be resident, so it is only
     // used when this chain is the sole lane, and its extra per-column parameters fit in smem up to 8 classes
     fuse = h->fuse && single_lane && Cp <= 8 && !slim;
