@@ -20,6 +20,7 @@
 // Tile geometries (all bit-identical, chosen per call by choose_ctas): 128 x 256 single-CTA tiles, 256 x 256 CTA-pair
 // tiles (+ 2 x 64-row half tiles), slim 128 x 128 single-CTA tiles for calls too small to fill the SMs.  Tile order
 // (plan_tiles): N-tile-major while a member's activations fit in L2, row-major beyond.
+#include <atomic>
 #include <cstdio>
 
 #include "ladine_internal.cuh"
@@ -940,6 +941,20 @@ uint32_t make_idesc(bool bf16, int ctas, int n = BN) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)((BM * ctas) >> 4) << 24);
 }
 
+// Run `fn` (a cudaFuncSetAttribute call) the first time a kernel instantiation is launched on the current device; `done`
+// is that instantiation's bitmask over device ordinals.
+template <typename Fn>
+cudaError_t configure_once(std::atomic<uint64_t>& done, Fn fn) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const uint64_t bit = dev < 64 ? (uint64_t)1 << dev : 0;
+  if (bit && (done.load(std::memory_order_acquire) & bit)) return cudaSuccess;
+  e = fn();
+  if (e == cudaSuccess && bit) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
+
 // Programmatic dependent launch is OPT-IN (ladine_set_option("pdl", 1)) and only ever applied to chains of
 // single-CTA kernels: measured neutral on B200 (the chain is bound by the shared-memory port and the power cap,
 // not by launch gaps), and PDL combined with cluster launches (CTA pairs) dead-locked the GPU after a few hundred
@@ -950,8 +965,12 @@ template <int LAYER, typename T16, int CP, int CTAS, int BNT = BN>
 cudaError_t launch_gemm_t(const GemmParams& p, int grid, bool pdl, cudaStream_t st) {
   const size_t smem = tensor_gemm_smem_bytes(CP);
   auto kern = trunk_gemm_kernel<LAYER, T16, CP, CTAS, BNT>;
-  // cheap (host-side table update); done per launch so it is right for every device of the process
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // once per (kernel instantiation, device): the call costs several microseconds of host time, which a chain of
+  // thousands of small launches cannot afford (a small call is bound by the host's launch rate, not by the GPU)
+  static std::atomic<uint64_t> configured{0};
+  cudaError_t e = configure_once(configured, [&] {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -1008,7 +1027,10 @@ template <int MODE, typename T16, int CP, int VEC>
 cudaError_t launch_tail_t(const TailHeadParams& p, dim3 grid, bool pdl, cudaStream_t st) {
   auto kern = tailhead_kernel<MODE, T16, CP, VEC>;
   // same shared-memory carveout as the GEMM kernels, so the SMs are not reconfigured at every kernel boundary
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  static std::atomic<uint64_t> configured{0};
+  cudaError_t e = configure_once(configured, [&] {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  });
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
