@@ -15,7 +15,11 @@
  *   - every call returns 0 on success or a negative ladine_status; nothing throws across the ABI;
  *     ladine_last_error() returns a human-readable message for the last failure on that handle;
  *   - work is enqueued on the caller's CUDA stream (cudaStream_t passed as void*); pointers are
- *     borrowed until that stream-ordered work completes; no hidden host synchronisation;
+ *     borrowed until that stream-ordered work completes.  ladine_sample / ladine_fill_noise never synchronise
+ *     with the host in steady state; the exceptions are stated where they occur: the first call that needs a
+ *     LARGER workspace than any earlier one (the old buffer is released after a device synchronisation),
+ *     ladine_free_member / ladine_destroy (device synchronisation before the buffers are freed) and
+ *     ladine_get_profile (waits for the recorded events);
  *   - a handle is bound to one device and is not re-entrant (the caller serialises calls per
  *     handle); distinct handles are independent.
  */
@@ -47,7 +51,11 @@ typedef enum {
   LADINE_PREC_AUTO = 0, /* FP32 SMEM-resident kernel when feature_dim <= 128, else FP16 tensor cores */
   LADINE_PREC_FP32 = 1, /* FP32 FFMA, weights resident in shared memory (feature_dim <= 128)         */
   LADINE_PREC_FP16 = 2, /* tcgen05 kind::f16, FP16 operands, FP32 accumulate in TMEM                 */
-  LADINE_PREC_BF16 = 3  /* tcgen05 kind::f16, BF16 operands, FP32 accumulate in TMEM                 */
+  LADINE_PREC_BF16 = 3, /* tcgen05 kind::f16, BF16 operands, FP32 accumulate in TMEM                 */
+  LADINE_PREC_FP32X = 4 /* FP32-grade on tensor cores for any feature_dim: every GEMM operand is split into
+                           FP16 hi + lo parts (W pre-scaled by a power of two) and each K slice issues three
+                           tcgen05.mma (hi.hi + hi.lo + lo.hi) into the same FP32 TMEM accumulator: ~3x the
+                           FP16 cost, error ~1e-6 relative (the reference is FP32: latent_model.py:169-184)  */
 } ladine_precision;
 
 /*

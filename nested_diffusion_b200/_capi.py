@@ -11,7 +11,7 @@ import threading
 
 LADINE_MAX_CLASSES = 16
 LADINE_MAX_GROUP = 8
-PREC = {"auto": 0, "fp32": 1, "fp16": 2, "bf16": 3}
+PREC = {"auto": 0, "fp32": 1, "fp16": 2, "bf16": 3, "fp32x": 4}
 PREC_NAME = {v: k for k, v in PREC.items()}
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libladine.so")

@@ -11,8 +11,7 @@ SRC = [os.path.join(HERE, "csrc", f) for f in ("ladine_api.cu", "ladine_resident
 HDR = [os.path.join(HERE, "csrc", f) for f in ("ladine_common.cuh", "ladine_internal.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "ladine.h")]
 OUT = os.path.join(HERE, "lib", "libladine.so")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-         "-Xcompiler", "-fPIC"]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def nvcc_path() -> str:
@@ -46,13 +45,44 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [nvcc_path()] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = os.path.join(HERE, "lib", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = nvcc_path()
+
+    def compile_one(src):
+        # one object per translation unit, compiled concurrently (each takes tens of seconds); an object whose source
+        # and headers did not change is reused
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        stamp = obj + ".srchash"
+        import hashlib
+        hh = hashlib.sha256(" ".join(FLAGS).encode())
+        for pth in [src] + HDR:
+            with open(pth, "rb") as f:
+                hh.update(f.read())
+        key = hh.hexdigest()
+        if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == key:
+            return obj, 0, ""
+        cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode == 0:
+            with open(stamp, "w") as f:
+                f.write(key + "\n")
+        return obj, r.returncode, r.stdout + r.stderr
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(SRC)) as ex:
+        results = list(ex.map(compile_one, SRC))
+    for obj, rc, log in results:
+        if rc != 0:
+            sys.stderr.write(log)
+            raise RuntimeError("nvcc failed compiling " + obj)
+        if verbose:
+            sys.stderr.write(log)
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] +
+                       [o for o, _, _ in results], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libladine.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("nvcc failed linking libladine.so")
     with open(STAMP, "w") as f:
         f.write(source_hash() + "\n")
     return OUT

@@ -30,9 +30,12 @@ int fail_cuda(ladine_handle* h, cudaError_t e, const char* what) {
 __global__ void fold_tables_kernel(const float* __restrict__ E, const float* __restrict__ lin_b,
                                    const float* __restrict__ bn_w, const float* __restrict__ bn_b,
                                    const float* __restrict__ bn_mean, const float* __restrict__ bn_var, float eps,
-                                   float gain, int T, int F, int Fp, float* __restrict__ A, float* __restrict__ Cc) {
+                                   float gain, const float* __restrict__ a_gain_dev, int T, int F, int Fp,
+                                   float* __restrict__ A, float* __restrict__ Cc) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)T * Fp) return;
+  // FP32X: the GEMM runs on W * 2^s, so the scale row carries 2^-s (a power of two: exact)
+  const float a_gain = a_gain_dev ? *a_gain_dev : 1.0f;
   const int f = (int)(i % Fp);
   const int t = (int)(i / Fp);
   float a = 0.f, c = 0.f;
@@ -42,7 +45,7 @@ __global__ void fold_tables_kernel(const float* __restrict__ E, const float* __r
     a = e * s;
     c = e * (s * lin_b[f]) + (bn_b[f] - s * bn_mean[f]);
   }
-  A[i] = a * gain;
+  A[i] = a * gain * a_gain;
   Cc[i] = c * gain;
 }
 
@@ -85,6 +88,44 @@ __global__ void convert_pad_kernel(const float* __restrict__ W, int F, int Fp, T
   if (i >= (size_t)Fp * Fp) return;
   const int n = (int)(i / Fp), k = (int)(i % Fp);
   out[i] = Pack16<T16>::one((n < F && k < F) ? W[(size_t)n * F + k] : 0.f);
+}
+
+// ---- FP32X: W = hi + lo in FP16 after scaling by a power of two ----
+// max |W| over the [F, F] matrix (non-negative floats order like their bit patterns)
+__global__ void absmax_kernel(const float* __restrict__ W, size_t n, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(W[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+// scale = 2^e with max|W| * 2^e in [2^13, 2^14): the hi part keeps 11 significant bits, the lo part (<= 2^-11 of hi)
+// stays far above the FP16 subnormal range for every weight that matters, and nothing overflows (65504 ~ 2^16)
+__global__ void split_scale_kernel(const unsigned int* __restrict__ absmax_bits, float* __restrict__ wscale) {
+  const int l = threadIdx.x;
+  if (l >= 2) return;
+  const float m = __uint_as_float(absmax_bits[l]);
+  int e = 0;
+  if (m > 0.f && isfinite(m)) {
+    int me;
+    frexpf(m, &me);        // m = f * 2^me, f in [0.5, 1)
+    e = 14 - me;           // m * 2^e in [2^13, 2^14)
+  }
+  e = max(-60, min(60, e));
+  wscale[l] = ldexpf(1.0f, e);
+  wscale[2 + l] = ldexpf(1.0f, -e);
+}
+// out[n, k] = fp16(w * s), out[n, Fp + k] = fp16(w * s - hi)      ([Fp, 2 * Fp], zero padded)
+__global__ void convert_split_kernel(const float* __restrict__ W, int F, int Fp, const float* __restrict__ scale,
+                                     __half* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)Fp * Fp) return;
+  const int n = (int)(i / Fp), k = (int)(i % Fp);
+  const float w = (n < F && k < F) ? W[(size_t)n * F + k] * (*scale) : 0.f;
+  const __half hi = Pack16<__half>::one(w);
+  const __half lo = Pack16<__half>::one(w - __half2float(hi));
+  out[(size_t)n * 2 * Fp + k] = hi;
+  out[(size_t)n * 2 * Fp + Fp + k] = lo;
 }
 
 // u[k, n, f] = sum_c W1g[f, c] * y_0_hat[k, n, c]   (the step-invariant half of lin1)
@@ -144,6 +185,7 @@ void free_member_buffers(ladine_member* m) {
   cudaFree(m->W3t);
   cudaFree(m->W2h);
   cudaFree(m->W3h);
+  cudaFree(m->wscale);
 }
 
 struct DeviceGuard {
@@ -297,8 +339,9 @@ int ladine_pack_member(ladine_handle* h, const ladine_member_desc* d, void* stre
   if (prec == LADINE_PREC_AUTO) prec = d->feature_dim <= 128 ? LADINE_PREC_FP32 : LADINE_PREC_FP16;
   if (prec == LADINE_PREC_FP32 && d->feature_dim > 128)
     return fail(h, LADINE_ERR_UNSUPPORTED,
-                "FP32 SMEM-resident path needs feature_dim <= 128 (two FP32 square layers must fit in shared memory)");
-  if (prec != LADINE_PREC_FP32 && prec != LADINE_PREC_FP16 && prec != LADINE_PREC_BF16)
+                "FP32 SMEM-resident path needs feature_dim <= 128 (two FP32 square layers must fit in shared memory); "
+                "use LADINE_PREC_FP32X (split-operand tensor cores, FP32-grade) for wider members");
+  if (prec != LADINE_PREC_FP32 && prec != LADINE_PREC_FP16 && prec != LADINE_PREC_BF16 && prec != LADINE_PREC_FP32X)
     return fail(h, LADINE_ERR_INVALID, "unknown precision");
 
   DeviceGuard guard(h->device);
@@ -313,6 +356,8 @@ int ladine_pack_member(ladine_handle* h, const ladine_member_desc* d, void* stre
   m->precision = prec;
   m->device = h->device;
   const bool tensor = prec != LADINE_PREC_FP32;
+  const bool split = prec == LADINE_PREC_FP32X;
+  m->split = split ? 1 : 0;
   m->Fp = tensor ? (int)align_up(m->F, 256) : (int)align_up(m->F, 32);
   const int F = m->F, Fp = m->Fp, T = m->T, Cp = m->Cp;
 
@@ -327,8 +372,9 @@ int ladine_pack_member(ladine_handle* h, const ladine_member_desc* d, void* stre
   ok(dmalloc(&m->W4, (size_t)Cp * Fp, &m->bytes));
   ok(dmalloc(&m->b4, (size_t)Cp, &m->bytes));
   if (tensor) {
-    ok(dmalloc(reinterpret_cast<uint16_t**>(&m->W2h), (size_t)Fp * Fp, &m->bytes));
-    ok(dmalloc(reinterpret_cast<uint16_t**>(&m->W3h), (size_t)Fp * Fp, &m->bytes));
+    ok(dmalloc(reinterpret_cast<uint16_t**>(&m->W2h), (size_t)Fp * Fp * (split ? 2 : 1), &m->bytes));
+    ok(dmalloc(reinterpret_cast<uint16_t**>(&m->W3h), (size_t)Fp * Fp * (split ? 2 : 1), &m->bytes));
+    if (split) ok(dmalloc(&m->wscale, 8, &m->bytes));   // [0..3] scales, [4..5] abs-max scratch (as uint bits)
   } else {
     ok(dmalloc(&m->W2t, (size_t)Fp * Fp, &m->bytes));
     ok(dmalloc(&m->W3t, (size_t)Fp * Fp, &m->bytes));
@@ -343,10 +389,18 @@ int ladine_pack_member(ladine_handle* h, const ladine_member_desc* d, void* stre
   const float gain = tensor ? kLog2e : 1.0f;
   const float* lin_b[3] = {d->lin1_b, d->lin2_b, d->lin3_b};
   const size_t tf = (size_t)T * Fp;
+  if (split) {
+    unsigned int* amax = reinterpret_cast<unsigned int*>(m->wscale + 4);
+    cudaMemsetAsync(amax, 0, 2 * sizeof(unsigned int), st);
+    absmax_kernel<<<296, 256, 0, st>>>(d->lin2_w, (size_t)F * F, amax);
+    absmax_kernel<<<296, 256, 0, st>>>(d->lin3_w, (size_t)F * F, amax + 1);
+    split_scale_kernel<<<1, 32, 0, st>>>(amax, m->wscale);
+  }
   for (int l = 0; l < 3; ++l) {
+    const float* a_gain = (split && l > 0) ? m->wscale + 2 + (l - 1) : nullptr;
     fold_tables_kernel<<<(unsigned)((tf + 255) / 256), 256, 0, st>>>(d->emb[l], lin_b[l], d->bn_w[l], d->bn_b[l],
-                                                                     d->bn_mean[l], d->bn_var[l], d->bn_eps, gain, T, F,
-                                                                     Fp, m->A[l], m->Cc[l]);
+                                                                     d->bn_mean[l], d->bn_var[l], d->bn_eps, gain, a_gain,
+                                                                     T, F, Fp, m->A[l], m->Cc[l]);
   }
   pack_small_kernel<<<(Fp * Cp + 255) / 256, 256, 0, st>>>(d->lin1_w, d->lin4_w, d->lin4_b, F, Fp, m->C, Cp, m->guidance,
                                                            m->W1y, m->W1g, m->W4, m->b4);
@@ -355,6 +409,9 @@ int ladine_pack_member(ladine_handle* h, const ladine_member_desc* d, void* stre
   if (!tensor) {
     transpose_pad_kernel<<<gff, 256, 0, st>>>(d->lin2_w, F, Fp, m->W2t);
     transpose_pad_kernel<<<gff, 256, 0, st>>>(d->lin3_w, F, Fp, m->W3t);
+  } else if (split) {
+    convert_split_kernel<<<gff, 256, 0, st>>>(d->lin2_w, F, Fp, m->wscale + 0, static_cast<__half*>(m->W2h));
+    convert_split_kernel<<<gff, 256, 0, st>>>(d->lin3_w, F, Fp, m->wscale + 1, static_cast<__half*>(m->W3h));
   } else if (prec == LADINE_PREC_FP16) {
     convert_pad_kernel<__half><<<gff, 256, 0, st>>>(d->lin2_w, F, Fp, static_cast<__half*>(m->W2h));
     convert_pad_kernel<__half><<<gff, 256, 0, st>>>(d->lin3_w, F, Fp, static_cast<__half*>(m->W3h));
@@ -439,6 +496,7 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
   const int F = m0->F, Fp = m0->Fp, C = m0->C, Cp = m0->Cp;
   const SlotInfo si = slot_info(*a);
   const bool tensor = m0->precision != LADINE_PREC_FP32;
+  const uint64_t act_cols = (uint64_t)Fp * (m0->split ? 2 : 1);   // FP32X: hi | lo halves per activation row
   h->last_launches = 0;
 
   const StepCoef* h_coef = reinterpret_cast<const StepCoef*>(a->coef);
@@ -465,8 +523,8 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
   const uint64_t o_u = lo; lo = align_up(lo + (uint64_t)gmax * a->N * Fp * 4, 1024);
   uint64_t o_h1 = 0, o_h2 = 0, o_part = 0, o_y = 0, o_sched = 0, o_arr = 0;
   if (tensor) {
-    o_h1 = lo; lo = align_up(lo + m_total * Fp * 2, 1024);
-    o_h2 = lo; lo = align_up(lo + m_total * Fp * 2, 1024);
+    o_h1 = lo; lo = align_up(lo + m_total * act_cols * 2, 1024);
+    o_h2 = lo; lo = align_up(lo + m_total * act_cols * 2, 1024);
     o_part = lo; lo = align_up(lo + m_total * (Fp / 256) * 2 * Cp * 4, 1024);
     o_sched = lo; lo = align_up(lo + sched_bytes_bound(gmax, rows, Fp / 128), 1024);
     o_arr = lo; lo = align_up(lo + (uint64_t)gmax * ((rows + 127) / 128 + 1) * 2 * sizeof(int), 1024);
@@ -689,7 +747,8 @@ int ladine_debug_layer(ladine_handle* h, const ladine_member* member, int layer,
   if (!h) return LADINE_ERR_INVALID;
   if (!member || !h_in || rows < 1 || (layer != 2 && layer != 3) || t < 0 || t >= member->T)
     return fail(h, LADINE_ERR_INVALID, "bad debug-layer arguments");
-  if (member->precision == LADINE_PREC_FP32) return fail(h, LADINE_ERR_UNSUPPORTED, "debug layer is for the tensor path");
+  if (member->precision == LADINE_PREC_FP32 || member->split)
+    return fail(h, LADINE_ERR_UNSUPPORTED, "debug layer is for the FP16 / BF16 tensor path");
   if ((layer == 2 && !h_out) || (layer == 3 && !part)) return fail(h, LADINE_ERR_INVALID, "missing output buffer");
   DeviceGuard guard(h->device);
   int rc = ensure_workspace(h, sched_bytes_bound(1, rows, member->Fp / 128));

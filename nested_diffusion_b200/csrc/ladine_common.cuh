@@ -109,24 +109,36 @@ __device__ __forceinline__ float posterior_step_op(const StepCoef& k, float y, f
   return __fadd_rn(m, __fmul_rn(k.sig, z));
 }
 
-// 16-bit operand packing for the tensor-core path
+// 16-bit operand packing for the tensor-core path.  Conversions SATURATE (cvt.rn.satfinite: one F2FP instruction,
+// |v| > max finite -> +-max finite, 65504 for FP16) instead of rounding to infinity: an overflowing activation would
+// otherwise reach the next tcgen05 GEMM as inf and come out as NaN (inf x mixed-sign weights).  NaN stays NaN.
 template <typename T>
 struct Pack16;
 template <>
 struct Pack16<__half> {
   static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
-    __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
   }
-  static __device__ __forceinline__ __half one(float v) { return __float2half_rn(v); }
+  static __device__ __forceinline__ __half one(float v) {
+    unsigned short r;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+    return __ushort_as_half(r);
+  }
 };
 template <>
 struct Pack16<__nv_bfloat16> {
   static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
+    uint32_t r;
+    asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
   }
-  static __device__ __forceinline__ __nv_bfloat16 one(float v) { return __float2bfloat16_rn(v); }
+  static __device__ __forceinline__ __nv_bfloat16 one(float v) {
+    unsigned short r;
+    asm("cvt.rn.satfinite.bf16.f32 %0, %1;" : "=h"(r) : "f"(v));
+    return __ushort_as_bfloat16(r);
+  }
 };
 
 }  // namespace ladine

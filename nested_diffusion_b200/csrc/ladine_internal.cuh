@@ -27,9 +27,13 @@ struct ladine_member {
   // FP32-resident path: k-major (transposed) FP32 weights  Wt[k * Fp + n] = W[n][k]
   float* W2t = nullptr;
   float* W3t = nullptr;
-  // tensor path: 16-bit [Fp, Fp] row-major ([out][in], K contiguous)
+  // tensor path: 16-bit [Fp, Fp] row-major ([out][in], K contiguous).  FP32X: [Fp, 2 * Fp] FP16, columns [0, Fp) hold
+  // the hi part and [Fp, 2 * Fp) the lo part of W * wscale[l] (wscale = a power of two that lifts max|W| to ~2^14 so
+  // that the lo parts stay normal FP16 numbers; its inverse is folded into the A_l scale rows)
   void* W2h = nullptr;
   void* W3h = nullptr;
+  float* wscale = nullptr;   // FP32X: device [4] = scale2, scale3, 1/scale2, 1/scale3
+  int split = 0;             // 1 for FP32X
   uint64_t bytes = 0;
 };
 

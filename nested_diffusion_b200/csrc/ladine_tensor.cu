@@ -174,6 +174,8 @@ struct TailHeadParams {
   int slot;            // noise slot / trajectory entry consumed-written by this launch
   int traj_entry;
   int N, D, C, Fin, Fp, NB, rows_pad, n_slots, n_traj, dchunk, write_out, colsplit;
+  int ld_h1;           // row stride of h1 in elements: Fp, or 2 * Fp in split (FP32X) mode
+  int split;           // FP32X: h1 is written as FP16 hi (columns [0, Fp)) + lo (columns [Fp, 2 * Fp)) parts
 };
 
 struct GemmParams {
@@ -185,6 +187,11 @@ struct GemmParams {
   void* h_out;                         // layer 2: [M_total, Fp] 16-bit
   float* part;                         // layer 3: [M_total, NB, Cp]
   int Fp, NB, KB;                      // padded feature dim, N tiles (Fp/256), K blocks (Fp/64)
+  // FP32X (split operands): A = [A_hi | A_lo] and W = [W_hi | W_lo] side by side (row stride 2 * Fp), and the K loop
+  // runs three segments over the same accumulator -- A_lo.W_hi, A_hi.W_lo, A_hi.W_hi (small terms first) -- i.e. a
+  // plain GEMM over an extended K: the pipeline, tile schedule and TMEM protocol are those of the 16-bit path.
+  int nseg;                            // 1, or 3 in split mode
+  int ld_out;                          // row stride of h_out in elements (Fp, or 2 * Fp in split mode)
   int rows;                            // valid rows per member
   int rows_pad;                        // row stride between members (multiple of 128 * CTAS)
   // static tile schedule: unit u (a CTA, or a CTA pair) runs sched[u * sched_stride + 0, 1, ...] until a -1.
@@ -242,6 +249,12 @@ __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&v)[8])
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
                "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
+}
+
+// FP32X: lo parts of two values whose FP16 hi parts are packed in `hi2`: fp16(v - float(hi))
+__device__ __forceinline__ uint32_t split_lo(uint32_t hi2, float v0, float v1) {
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+  return Pack16<__half>::pack(v0 - h.x, v1 - h.y);
 }
 
 // ---- programmatic dependent launch (PDL) ----
@@ -502,20 +515,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
         const int arow = tc.member * p.rows_pad + tc.mb * (BM * CTAS) + (int)rank * (tc.half ? BM / 2 : BM);
         const int brow = tc.nb * BNT + (int)rank * Cfg::kBRows;
         const CUtensorMap* tb = &p.tmB[tc.member];
-        for (int kb = 0; kb < p.KB; ++kb) {
-          mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u, 0);
-          const uint32_t fb = smem_u32(&bars->full[stage]);
-          if (CTAS == 1) {
-            mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
-            tma_load_2d(smem_u32(sA + stage * Cfg::kABytes), &p.tmA, fb, kb * BK, arow);
-            tma_load_2d(smem_u32(sB + stage * Cfg::kBBytes), tb, fb, kb * BK, brow);
-          } else {
-            const uint32_t lfb = mapa_rank(fb, 0);  // both CTAs' bytes complete on the leader's barrier
-            if (rank == 0) mbar_arrive_expect_tx(fb, 2 * Cfg::kStageBytes);
-            tma_load_2d_pair(smem_u32(sA + stage * Cfg::kABytes), &p.tmA, lfb, kb * BK, arow);
-            tma_load_2d_pair(smem_u32(sB + stage * Cfg::kBBytes), tb, lfb, kb * BK, brow);
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          // split mode: segment 0 = A_lo . W_hi, 1 = A_hi . W_lo, 2 = A_hi . W_hi; the lo halves start at column Fp
+          const int acol0 = (p.nseg == 3 && seg == 0) ? p.Fp : 0;
+          const int bcol0 = (p.nseg == 3 && seg == 1) ? p.Fp : 0;
+          for (int kb = 0; kb < p.KB; ++kb) {
+            mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u, 0);
+            const uint32_t fb = smem_u32(&bars->full[stage]);
+            if (CTAS == 1) {
+              mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+              tma_load_2d(smem_u32(sA + stage * Cfg::kABytes), &p.tmA, fb, acol0 + kb * BK, arow);
+              tma_load_2d(smem_u32(sB + stage * Cfg::kBBytes), tb, fb, bcol0 + kb * BK, brow);
+            } else {
+              const uint32_t lfb = mapa_rank(fb, 0);  // both CTAs' bytes complete on the leader's barrier
+              if (rank == 0) mbar_arrive_expect_tx(fb, 2 * Cfg::kStageBytes);
+              tma_load_2d_pair(smem_u32(sA + stage * Cfg::kABytes), &p.tmA, lfb, acol0 + kb * BK, arow);
+              tma_load_2d_pair(smem_u32(sB + stage * Cfg::kBBytes), tb, lfb, bcol0 + kb * BK, brow);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -533,7 +551,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
         mbar_wait(smem_u32(&bars->acc_empty[as]), aphase ^ 1u, 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BNT);
-        for (int kb = 0; kb < p.KB; ++kb) {
+        const int kblocks = p.KB * p.nseg;   // split mode: three K segments into the same accumulator
+        for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(smem_u32(&bars->full[stage]), phase, 2);
           tc_fence_after();
           const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * Cfg::kABytes));
@@ -640,13 +659,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
           if (LAYER == 2) {
             if (valid) {
               // 32 consecutive 16-bit outputs of this row = 64 B = two full 32-byte sectors: 256-bit stores
-              T16* dst = reinterpret_cast<T16*>(p.h_out) + grow * p.Fp + nb * BNT + ocol;
+              T16* dst = reinterpret_cast<T16*>(p.h_out) + grow * p.ld_out + nb * BNT + ocol;
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
                 uint32_t o[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] = Pack16<T16>::pack(hcol[16 * q + 2 * i], hcol[16 * q + 2 * i + 1]);
                 st_global_256(dst + 16 * q, o);
+                if (p.nseg == 3) {   // FP32X: the residual of the FP16 rounding goes to the lo half (warp-uniform branch)
+                  uint32_t ol[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) ol[i] = split_lo(o[i], hcol[16 * q + 2 * i], hcol[16 * q + 2 * i + 1]);
+                  st_global_256(dst + p.Fp + 16 * q, ol);
+                }
               }
             }
           } else {
@@ -862,8 +887,8 @@ __global__ void __launch_bounds__(kTailThreads, (CP <= 4 ? 8 : 1)) tailhead_kern
         for (int c = 0; c < CP; ++c) pc[j][c] = a1[j] * __ldg(p.W1y[k] + (size_t)(f0 + j) * CP + c);  // padded classes: 0
       }
     }
-    T16* hrow = reinterpret_cast<T16*>(p.h1) + ((size_t)k * p.rows_pad + (size_t)n * p.D + d0) * p.Fp + f0;
-    for (int dl = 0; dl < nd; ++dl, hrow += p.Fp) {
+    T16* hrow = reinterpret_cast<T16*>(p.h1) + ((size_t)k * p.rows_pad + (size_t)n * p.D + d0) * p.ld_h1 + f0;
+    for (int dl = 0; dl < nd; ++dl, hrow += p.ld_h1) {
       float yv[CP];
 #pragma unroll
       for (int c = 0; c < CP; ++c) yv[c] = sY[dl * CP + c];   // padded classes hold 0
@@ -883,11 +908,25 @@ __global__ void __launch_bounds__(kTailThreads, (CP <= 4 ? 8 : 1)) tailhead_kern
         o.z = Pack16<T16>::pack(hv[VEC - 4], hv[VEC - 3]);
         o.w = Pack16<T16>::pack(hv[VEC - 2], hv[VEC - 1]);
         *reinterpret_cast<uint4*>(hrow) = o;
+        if (p.split) {
+          uint4 l;
+          l.x = split_lo(o.x, hv[0], hv[1]);
+          l.y = split_lo(o.y, hv[2], hv[3]);
+          l.z = split_lo(o.z, hv[VEC - 4], hv[VEC - 3]);
+          l.w = split_lo(o.w, hv[VEC - 2], hv[VEC - 1]);
+          *reinterpret_cast<uint4*>(hrow + p.Fp) = l;
+        }
       } else {
         uint2 o;
         o.x = Pack16<T16>::pack(hv[0], hv[1]);
         o.y = Pack16<T16>::pack(hv[2], hv[3]);
         *reinterpret_cast<uint2*>(hrow) = o;
+        if (p.split) {
+          uint2 l;
+          l.x = split_lo(o.x, hv[0], hv[1]);
+          l.y = split_lo(o.y, hv[2], hv[3]);
+          *reinterpret_cast<uint2*>(hrow + p.Fp) = l;
+        }
       }
     }
   }
@@ -1249,6 +1288,7 @@ struct TensorChain {
     st = st_;
     const ladine_member* m0 = members[0];
     bf16 = m0->precision == LADINE_PREC_BF16;
+    const bool split = m0->split != 0;
     Fp = m0->Fp;
     Cp = m0->Cp;
     K = a.K;
@@ -1260,7 +1300,7 @@ struct TensorChain {
     pdl = pdl_allowed(h, cpu);
     // the fused tail + head spins on other CTAs of the same launch: every CTA must be resident, so it is only
     // used when this chain is the sole lane, and its extra per-column parameters fit in smem up to 8 classes
-    fuse = h->fuse && single_lane && Cp <= 8 && !slim;
+    fuse = h->fuse && single_lane && Cp <= 8 && !slim && !split;
     const int NBt = Fp / bnt;                   // column tiles per row tile
     if ((rows + BM - 1) / BM > 4096 || NBt > 1024) {
       *err = "too many rows per member for one launch group (max 524288 chains): tile the images (NestedEnsemble does)";
@@ -1270,7 +1310,7 @@ struct TensorChain {
     // a member's activations (rows x Fp 16-bit) stay in L2, but beyond that every N tile re-reads them from HBM
     // (F/256 = 16 passes at the shipped width).  Row-major runs the F/256 column tiles of a few row tiles together:
     // the activations are read once and the member's 32 MiB W cycles through L2.  "order" option: 0 auto, 1 / 2 force.
-    const size_t act_bytes = (size_t)((rows + BM - 1) / BM) * BM * Fp * 2;
+    const size_t act_bytes = (size_t)((rows + BM - 1) / BM) * BM * Fp * 2 * (split ? 2 : 1);
     const bool row_major = h->order == 2 || (h->order == 0 && act_bytes > kRowMajorActBytes);
     const TilePlan plan = plan_tiles(K, rows, NBt, cpu, h->sm_count / cpu, row_major);
     const TilePlan plan3 = (fuse && !row_major) ? plan_tiles(K, rows, NBt, cpu, h->sm_count / cpu, /*row_major=*/true) : plan;
@@ -1288,14 +1328,17 @@ struct TensorChain {
     if (e == cudaSuccess && fuse)
       e = cudaMemsetAsync(ws.arrivals, 0, sizeof(int) * (size_t)K * mblk_total * cpu, st);
     if (e != cudaSuccess) return e;
-    if (!make_tmap(h, &g2.tmA, ws.h1, m_total, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
-    if (!make_tmap(h, &g3.tmA, ws.h2, m_total, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
+    const uint64_t ld = (uint64_t)Fp * (split ? 2 : 1);   // FP32X: [hi | lo] halves side by side
+    if (!make_tmap(h, &g2.tmA, ws.h1, m_total, ld, BM, bf16, err)) return cudaErrorInvalidValue;
+    if (!make_tmap(h, &g3.tmA, ws.h2, m_total, ld, BM, bf16, err)) return cudaErrorInvalidValue;
     for (int k = 0; k < K; ++k) {
-      if (!make_tmap(h, &g2.tmB[k], members[k]->W2h, Fp, Fp, bnt / cpu, bf16, err)) return cudaErrorInvalidValue;
-      if (!make_tmap(h, &g3.tmB[k], members[k]->W3h, Fp, Fp, bnt / cpu, bf16, err)) return cudaErrorInvalidValue;
+      if (!make_tmap(h, &g2.tmB[k], members[k]->W2h, Fp, ld, bnt / cpu, bf16, err)) return cudaErrorInvalidValue;
+      if (!make_tmap(h, &g3.tmB[k], members[k]->W3h, Fp, ld, bnt / cpu, bf16, err)) return cudaErrorInvalidValue;
       g3.W4[k] = members[k]->W4;
     }
     for (GemmParams* g : {&g2, &g3}) {
+      g->nseg = split ? 3 : 1;
+      g->ld_out = (int)ld;
       g->Fp = Fp;
       g->NB = Fp / BN;   // 256-column groups: the lin4 partial buffer has 2 * NB slots per row whatever the tile width
       g->KB = Fp / BK;
@@ -1341,6 +1384,8 @@ struct TensorChain {
     tp.C = m0->C;
     tp.Fin = m0->F;
     tp.Fp = Fp;
+    tp.ld_h1 = (int)ld;
+    tp.split = split ? 1 : 0;
     tp.NB = Fp / BN;
     tp.rows_pad = rows_pad;
     tp.n_slots = n_slots;
@@ -1481,6 +1526,8 @@ cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int lay
   g.h_out = h_out;
   g.part = part;
   g.Fp = Fp;
+  g.nseg = 1;
+  g.ld_out = Fp;
   g.NB = Fp / BN;
   g.KB = Fp / BK;
   g.rows = rows;

@@ -193,6 +193,11 @@ def encode_features(model, x: torch.Tensor, mode: str = "fp32") -> torch.Tensor:
         return model.norm(model.encoder_x(x))
 
 
+def encoder_backend(model) -> str:
+    """What evaluates ``norm(encoder_x(x))`` for this model (reported by bench.py)."""
+    return "PyTorch FP32 GEMMs (cuBLAS)"
+
+
 _XF_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 

@@ -127,7 +127,9 @@ def sample_ensemble(models_or_ensemble, x, y0hats, draws, n_steps, alphas, one_m
     Every rank passes the SAME full ``x`` [N, ...] and ``y0hats`` [K, N, C]; each samples its image
     tile (``shard_bounds``) for all members and draws with Philox streams keyed on global
     (member, draw, image) ids -- so the gathered result is identical for any world size -- and
-    returns on every rank ``(y0 [N, K*D, C], probs [N, K*D, C] or None)`` in image-major order."""
+    returns on every rank ``(y0 [N, K*D, C], probs [N, K*D, C] or None)`` in image-major order.
+    ``x`` / ``y0hats`` may live on the HOST (pinned memory makes the copy asynchronous): only this rank's
+    image tile is copied to the device."""
     import torch.distributed as dist
 
     ens = models_or_ensemble if isinstance(models_or_ensemble, NestedEnsemble) else NestedEnsemble(
@@ -147,7 +149,12 @@ def sample_ensemble(models_or_ensemble, x, y0hats, draws, n_steps, alphas, one_m
     K, D = ens.K, int(draws)
     C = y0hats.shape[-1]
     if hi > lo:
-        res = ens.sample(x[lo:hi], y0hats[:, lo:hi], D, n_steps, alphas, one_minus_alphas_bar_sqrt, seed=seed,
+        x_local, yh_local = x[lo:hi], y0hats[:, lo:hi]
+        if x_local.device != ens.device:
+            x_local = x_local.to(ens.device, non_blocking=True)
+        if yh_local.device != ens.device:
+            yh_local = yh_local.to(ens.device, non_blocking=True)
+        res = ens.sample(x_local, yh_local, D, n_steps, alphas, one_minus_alphas_bar_sqrt, seed=seed,
                          temperature=temperature, image_offset=lo, images_total=N)
         y_local = res.y0.permute(2, 0, 1, 3).reshape(hi - lo, K * D, C)
         p_local = res.probs.permute(2, 0, 1, 3).reshape(hi - lo, K * D, C) if res.probs is not None else None

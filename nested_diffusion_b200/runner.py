@@ -71,9 +71,12 @@ def ensemble_metrics(cache: SampleCache, temperature: float) -> Dict[str, torch.
     pred_mc = torch.cat(cache.y0, dim=1)  # [S, N_total, C]  (:791-794)
     piw_ok, piw_ko = stats.compute_mean_piws_for_class(pred_mc, mv, target)
     var_ok, var_ko = stats.calculate_variances(pred_mc, mv, target)
-    return {"accuracy": stats.compute_accuracy(mv, target), "ece": stats.compute_ece(prob, target).cpu(),
-            "piw_correct": piw_ok, "piw_incorrect": piw_ko, "var_correct": var_ok, "var_incorrect": var_ko,
-            "majority_vote": mv.cpu(), "ensemble_prob": prob.cpu()}
+    out = {"accuracy": stats.compute_accuracy(mv, target), "ece": stats.compute_ece(prob, target),
+           "piw_correct": piw_ok, "piw_incorrect": piw_ko, "var_correct": var_ok, "var_incorrect": var_ko,
+           "majority_vote": mv, "ensemble_prob": prob}
+    # every statistic above ran on the device holding the gathered samples; only the (small) results of the report
+    # cross to the host, once (the reference moves all K*D sample tensors, classification_train_separately.py:783-784)
+    return {k: v.cpu() for k, v in out.items()}
 
 
 class NestedDiffusionTester:

@@ -59,43 +59,45 @@ def compute_ece(probs: torch.Tensor, target: torch.Tensor, n_bins: int = 10) -> 
     return torch.sum(gap * count / count.sum())
 
 
-def _masked_mean(values: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
-    return values[mask].mean()  # NaN for an empty selection, as in the reference
+def _group_means(values: torch.Tensor, cls: torch.Tensor, mask: torch.Tensor, C: int, empty: float) -> torch.Tensor:
+    """Per-class mean of ``values[n]`` over the instances with ``mask[n]`` and class ``cls[n]`` -> [C] on the
+    samples' device (one scatter-add, no per-class host loop); classes without such an instance get ``empty``."""
+    w = mask.to(values.dtype)
+    idx = cls.to(torch.int64)
+    total = torch.zeros(C, dtype=values.dtype, device=values.device).index_add_(0, idx, torch.where(mask, values, 0.0))
+    count = torch.zeros(C, dtype=values.dtype, device=values.device).index_add_(0, idx, w)
+    return torch.where(count > 0, total / count.clamp(min=1), torch.full_like(total, empty))
 
 
 def compute_mean_piws_for_class(prediction_tensors: Samples, mv: torch.Tensor, label: torch.Tensor):
-    """Mean 2.5-97.5 % interval width of the predicted class, split by class and by correctness."""
-    s = as_sample_tensor(prediction_tensors).detach().float().cpu()
-    mv, label = mv.detach().cpu(), label.detach().cpu()
-    lo = torch.quantile(s, q=0.025, dim=0)
-    hi = torch.quantile(s, q=0.975, dim=0)
-    piw = (hi - lo)[torch.arange(s.shape[1]), mv]
+    """Mean 2.5-97.5 % interval width of the predicted class, split by class and by correctness -> two [C] tensors.
+    A class with no (in)correct prediction gets NaN, as the reference's mean over an empty selection does
+    (classification_train_separately.py:102-140).  Unlike the reference nothing is copied to the host: the quantiles
+    and the per-class means run on the device that holds the gathered samples."""
+    s = as_sample_tensor(prediction_tensors).detach().float()
+    mv, label = mv.detach().to(s.device), label.detach().to(s.device)
+    q = torch.quantile(s, torch.tensor([0.025, 0.975], dtype=s.dtype, device=s.device), dim=0)   # [2, N, C]
+    piw = (q[1] - q[0]).gather(1, mv.view(-1, 1).to(torch.int64)).squeeze(1)                      # predicted class
     C = s.shape[2]
-    correct, incorrect = torch.zeros(C), torch.zeros(C)
-    for c in range(C):
-        sel = mv == c
-        correct[c] = _masked_mean(piw, sel & (mv == label))
-        incorrect[c] = _masked_mean(piw, sel & (mv != label))
-    return correct, incorrect
+    hit = mv == label
+    return (_group_means(piw, mv, hit, C, float("nan")), _group_means(piw, mv, ~hit, C, float("nan")))
 
 
 def calculate_variances(model_logits: Samples, predicted_classes: torch.Tensor, ground_truth: torch.Tensor):
-    """Across-chain variance of the predicted class' output, averaged over correct / incorrect instances."""
-    s = as_sample_tensor(model_logits).detach().float().cpu()
-    pred, truth = predicted_classes.detach().cpu(), ground_truth.detach().cpu()
+    """Across-chain (unbiased) variance of the predicted class' output, averaged over the correct / incorrect
+    instances of each class -> two [C] tensors, 0 where a class has none (classification_train_separately.py:143-174).
+    Runs on the samples' device."""
+    s = as_sample_tensor(model_logits).detach().float()
+    pred, truth = predicted_classes.detach().to(s.device), ground_truth.detach().to(s.device)
     C = s.shape[2]
-    correct, incorrect = torch.zeros(C), torch.zeros(C)
-    for c in range(C):
-        ok = (pred == c) & (truth == c)
-        ko = (pred == c) & (truth != c)
-        if ok.any():
-            correct[c] = s[:, ok, c].var(dim=0).mean()
-        if ko.any():
-            incorrect[c] = s[:, ko, c].var(dim=0).mean()
-    return correct, incorrect
+    own = s.gather(2, pred.view(1, -1, 1).expand(s.shape[0], -1, 1).to(torch.int64)).squeeze(2)   # [S, N]
+    var = own.var(dim=0)                                                                          # NaN when S == 1
+    hit = pred == truth
+    return _group_means(var, pred, hit, C, 0.0), _group_means(var, pred, ~hit, C, 0.0)
 
 
 def compute_accuracy(predictions: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
-    """classification_train_separately.py:801-807."""
-    predictions, labels = predictions.detach().cpu(), labels.detach().cpu()
+    """classification_train_separately.py:801-807 (a 0-dim tensor on the predictions' device)."""
+    predictions = predictions.detach()
+    labels = labels.detach().to(predictions.device)
     return torch.sum(predictions == labels).float() / predictions.numel()

@@ -160,6 +160,13 @@ class _Eps:
         self.sd, self.x, self.hoist = sd, x, hoist
         self.xf = encoder_features(sd, x) if hoist else None
 
+    @classmethod
+    def from_features(cls, sd: StateDict, xf: torch.Tensor) -> "_Eps":
+        """Hoisted provider for callers that already hold xf = norm(encoder_x(x)) (no encoder keys needed)."""
+        self = cls.__new__(cls)
+        self.sd, self.x, self.hoist, self.xf = sd, None, True, xf
+        return self
+
     def __call__(self, y, t, yhat):
         if self.hoist:
             return trunk_forward(self.sd, self.xf, y, t, yhat)
@@ -205,7 +212,7 @@ def p_sample_loop(sd: StateDict, x, y_0_hat, y_T_mean, n_steps: int, alphas, oma
                   noise: torch.Tensor, only_last_sample: bool = False, hoist: bool = False):
     """diffusion_utils.py:133-163.  ``noise``: [n_steps, B, C]."""
     assert noise.shape[0] >= n_steps
-    eps_fn = _Eps(sd, x, hoist)
+    eps_fn = x if isinstance(x, _Eps) else _Eps(sd, x, hoist)   # an _Eps (e.g. _Eps.from_features) may be passed as x
     cur = noise[0] + y_T_mean
     seq = [cur]
     for k, t in enumerate(reversed(range(1, n_steps)), start=1):
@@ -269,7 +276,21 @@ def fold_member(sd: StateDict, n_steps: int, dtype=torch.float32) -> Dict[str, t
 
 
 def _round_to(x: torch.Tensor, operand_dtype) -> torch.Tensor:
-    return x if operand_dtype is None else x.to(operand_dtype).to(x.dtype)
+    """Round to the GEMM operand type the way the kernels do: round-to-nearest-even, SATURATING at the largest finite
+    value (cvt.rn.satfinite), so an activation beyond 65504 in FP16 becomes 65504, not inf."""
+    if operand_dtype is None:
+        return x
+    if operand_dtype == "fp16x2":
+        # the FP32X path: operand = FP16 hi + FP16 lo (the sum is exact in FP32: 22 significant bits); the kernel also
+        # pre-scales W by a power of two so its lo parts stay normal -- emulated here by splitting a scaled copy
+        m = float(x.abs().max())
+        scale = 2.0 ** (14 - math.frexp(m)[1]) if (m > 0 and math.isfinite(m) and x.dim() == 2 and x.shape[0] == x.shape[1]) else 1.0
+        xs = x * scale
+        hi = xs.clamp(-65504, 65504).to(torch.float16).to(x.dtype)
+        lo = (xs - hi).clamp(-65504, 65504).to(torch.float16).to(x.dtype)
+        return (hi + lo) / scale
+    lim = torch.finfo(operand_dtype).max
+    return x.clamp(-lim, lim).to(operand_dtype).to(x.dtype)
 
 
 def packed_sample(sd: StateDict, xf, y_0_hat, y_T_mean, n_steps: int, alphas, omabs, noise,

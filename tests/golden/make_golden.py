@@ -155,14 +155,23 @@ def shipped_dims_fixture(name, *, B=8, steps=(999, 500, 1), sd_seed=0, in_seed=5
          xf_sample=xf[:, :64].contiguous())
 
 
-def trained_fixture(name, *, F, H, Dx, C, T, B, seed, train_steps=800):
+def trained_fixture(name, *, F, H, Dx, C, T, B, seed, train_steps=800, frozen_big=False, keep=None):
     """A member TRAINED with the reference's own objective (classification_train_separately.py:945-975:
     antithetic t, q_sample, MSE between the injected noise and eps_theta) on a toy two-cluster problem, so
     that eps_theta really predicts the noise and y_0 = O(1): the setting in which the north-star bar
-    "max-abs <= 1e-4 on final y_0" is meaningful.  The trained state_dict is stored verbatim."""
+    "max-abs <= 1e-4 on final y_0" is meaningful.  The trained state_dict is stored verbatim -- except with
+    ``frozen_big`` (the shipped width F=4096, where W2/W3 alone are 128 MB): there the member starts from
+    ``synth_state_dict(seed)``, its two square weights and three gamma tables stay FROZEN at those seeded values
+    (re-generated at test time, checksum-guarded) and only the small tensors are trained and stored ("sd/" overlay)."""
     t0 = time.time()
     torch.manual_seed(seed)
     model = ref_lm.ConditionalModel(ref_config(F, H, Dx, C, T), guidance=True)
+    big = ("lin2.lin.weight", "lin3.lin.weight", "lin1.embed.weight", "lin2.embed.weight", "lin3.embed.weight")
+    if frozen_big:
+        model.load_state_dict(orc.synth_state_dict(seed, F, H, Dx, C, T))
+        for k, p_ in model.named_parameters():
+            if k in big:
+                p_.requires_grad_(False)
     alphas, omabs = schedule(T)
     alphas_bar_sqrt = torch.sqrt(alphas.cumprod(0))
     g = torch.Generator().manual_seed(seed + 1)
@@ -175,7 +184,7 @@ def trained_fixture(name, *, F, H, Dx, C, T, B, seed, train_steps=800):
         yhat = torch.softmax(3.0 * (y0 + 0.6 * torch.randn(n, C, generator=g)), dim=1)   # imperfect guidance
         return x, y0, yhat, lab
 
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    opt = torch.optim.Adam([p_ for p_ in model.parameters() if p_.requires_grad], lr=1e-3)
     model.train()
     for it in range(train_steps):
         x, y0, yhat, _ = batch(128)
@@ -197,12 +206,13 @@ def trained_fixture(name, *, F, H, Dx, C, T, B, seed, train_steps=800):
         seq = torch.stack(ref_du.p_sample_loop(model, x, yhat, yhat, T, alphas, omabs, only_last_sample=False))
     noise = replay_noise(seed + 2, T, (B, C))
     acc = float((seq[-1].argmax(1) == lab).float().mean())
+    keep = list(range(T + 1)) if keep is None else sorted(set(keep))
     meta = dict(kind="chain", F=F, H=H, Dx=Dx, C=C, T=T, B=B, guidance=True, sd_seed=seed, in_seed=seed + 1,
-                noise_seed=seed + 2, eps_gain=1.0, keep=list(range(T + 1)), sched="linear", stored_inputs=True,
+                noise_seed=seed + 2, eps_gain=1.0, keep=keep, sched="linear", stored_inputs=True,
                 trained=True, train_steps=train_steps, final_loss=float(loss), accuracy=acc,
-                sd_digest=sd_digest(sd), in_digest=digest(x, yhat))
-    arrays = dict(traj=seq, y0=seq[-1], x=x, yhat=yhat, noise=noise, labels=lab)
-    arrays.update({"sd/" + k: v for k, v in sd.items()})
+                sd_digest=sd_digest(sd), in_digest=digest(x, yhat), sd_overlay=bool(frozen_big))
+    arrays = dict(traj=seq[keep], y0=seq[-1], x=x, yhat=yhat, noise=noise, labels=lab)
+    arrays.update({"sd/" + k: v for k, v in sd.items() if not (frozen_big and k in big)})
     save(name, meta, **arrays)
     print(f"  {name}: loss {float(loss):.4f} acc {acc:.3f} |y0|max={seq[-1].abs().max():.3f}  {time.time() - t0:.1f}s")
 
@@ -238,7 +248,113 @@ def layout_fixture(name="state_dict_layout"):
     save(name, dict(kind="layout", F=8, H=6, Dx=10, T=5, layouts=layouts), **arrays)
 
 
+def _reference_runner_functions():
+    """The runner module (classification_train_separately.py) cannot be imported here (matplotlib, statsmodels,
+    torchmetrics, foolbox, autoattack are absent), but its statistics are plain top-level / method ``def``s that
+    only use torch: lift their source with ``ast`` and execute THOSE definitions, unmodified."""
+    import ast
+    import types
+
+    path = "/root/reference/diffusion/classification_train_separately.py"
+    src = open(path).read()
+    tree = ast.parse(src)
+    want_top = {"majority_voting_for_mc_samples", "compute_mean_piws_for_class", "calculate_variances"}
+    want_meth = {"convert_to_prob", "compute_ensemble_confidence"}
+    picked = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in want_top]
+    for n in tree.body:
+        if isinstance(n, ast.ClassDef) and n.name == "Diffusion":
+            picked += [m for m in n.body if isinstance(m, ast.FunctionDef) and m.name in want_meth]
+    assert {n.name for n in picked} == want_top | want_meth
+    mod = types.ModuleType("ref_runner_extract")
+    mod.__dict__["torch"] = torch
+    code = compile(ast.Module(body=picked, type_ignores=[]), path, "exec")
+    exec(code, mod.__dict__)
+    return mod, {n.name: [n.lineno, n.end_lineno] for n in picked}
+
+
+def stats_fixture(name="stats_reference"):
+    """Ensemble statistics of the runner (classification_train_separately.py:51-68 majority vote, :102-140 PIW,
+    :143-174 variances, :392-398 convert_to_prob, :425-447 ensemble confidence) executed from the reference's own
+    source on seeded sample sets, including vote ties, classes nobody predicts and classes never correct."""
+    ref, lines = _reference_runner_functions()
+    fake_self = ns(temperature=None)
+    fake_self.convert_to_prob = lambda logits: ref.convert_to_prob(fake_self, logits)
+    arrays, cases = {}, []
+    g = torch.Generator().manual_seed(2024)
+
+    def add(tag, samples, label, temperature):
+        S = samples.shape[0]
+        lst = [samples[i].clone() for i in range(S)]
+        mv = ref.majority_voting_for_mc_samples(lst)
+        piw_c, piw_i = ref.compute_mean_piws_for_class(lst, mv, label)
+        var_c, var_i = ref.calculate_variances(lst, mv, label)
+        fake_self.temperature = temperature
+        prob = ref.convert_to_prob(fake_self, samples.clone())
+        conf = ref.compute_ensemble_confidence(fake_self, [samples[i].clone() for i in range(S)])
+        arrays.update({f"{tag}/samples": samples, f"{tag}/label": label, f"{tag}/mv": mv, f"{tag}/piw_correct": piw_c,
+                       f"{tag}/piw_incorrect": piw_i, f"{tag}/var_correct": var_c, f"{tag}/var_incorrect": var_i,
+                       f"{tag}/prob": prob, f"{tag}/conf": conf})
+        cases.append(dict(tag=tag, S=S, N=samples.shape[1], C=samples.shape[2], temperature=temperature))
+
+    # K*D = 100 chains, 70 images, 2 classes (the runner's shape), values around the one-hot targets
+    lab = torch.randint(0, 2, (70,), generator=g)
+    s = torch.nn.functional.one_hot(lab, 2).float()[None] + 0.8 * torch.randn(100, 70, 2, generator=g)
+    add("runner_shape", s, lab, 0.1737)
+    # exact vote ties (even S): instance i gets S/2 votes for two classes -> smallest label must win
+    s = torch.randn(10, 12, 3, generator=g)
+    for i in range(12):
+        a, b = i % 3, (i + 1 + i // 3) % 3
+        if a == b:
+            b = (b + 1) % 3
+        s[:5, i] = -1.0
+        s[:5, i, a] = 2.0
+        s[5:, i] = -1.0
+        s[5:, i, b] = 2.0
+    add("ties_c3", s, torch.randint(0, 3, (12,), generator=g), 0.3162)
+    # a class nobody predicts (NaN PIW means, zero variances) and a class that is never right
+    s = torch.randn(20, 30, 4, generator=g)
+    s[:, :, 3] = -5.0                       # class 3 never wins
+    lab = torch.randint(0, 3, (30,), generator=g)
+    lab[lab == 1] = 0                       # label 1 never occurs: predictions of class 1 are all incorrect
+    add("empty_classes_c4", s, lab, 0.5)
+    # a single chain (S = 1): variance is NaN in torch (unbiased), quantiles degenerate
+    s = torch.randn(1, 9, 2, generator=g)
+    add("single_chain", s, torch.randint(0, 2, (9,), generator=g), 1.0)
+    # ten classes, many chains
+    s = torch.randn(64, 40, 10, generator=g) * 2
+    add("c10", s, torch.randint(0, 10, (40,), generator=g), 0.25)
+    save(name, dict(kind="stats", cases=cases, reference_lines=lines), **arrays)
+
+
+def aux_fixture(name="aux_qsample_y0reparam"):
+    """diffusion_utils.q_sample (:39-50), y_0_reparam (:114-130) and extract (:31-35) of the reference with PER-ROW
+    timesteps (the training-side call shape, classification_train_separately.py:945-969) on a tiny reference member."""
+    F, H, Dx, C, T, B = 16, 8, 12, 3, 40, 10
+    sd = orc.synth_state_dict(131, F, H, Dx, C, T)
+    model = ref_member(sd, F, H, Dx, C, T, True)
+    alphas, omabs = schedule(T)
+    alphas_bar_sqrt = torch.cumprod(alphas, 0).sqrt()
+    g = torch.Generator().manual_seed(132)
+    x = torch.rand(B, Dx, generator=g)
+    y0 = torch.nn.functional.one_hot(torch.randint(0, C, (B,), generator=g), C).float()
+    yhat = torch.softmax(torch.randn(B, C, generator=g), 1)
+    t = torch.randint(0, T, (B,), generator=g)
+    noise = torch.randn(B, C, generator=g)
+    with torch.no_grad():
+        y_t = ref_du.q_sample(y0, yhat, alphas_bar_sqrt, omabs, t, noise=noise)
+        torch.manual_seed(133)
+        y_t_rng = ref_du.q_sample(y0, yhat, alphas_bar_sqrt, omabs, t)          # noise=None: randn_like(y)
+        y0r = ref_du.y_0_reparam(model, x, y_t, yhat, yhat, t, omabs)
+        ext = ref_du.extract(omabs, t, y_t)
+    arrays = {"sd/" + k: v for k, v in sd.items()}
+    arrays.update(x=x, y0=y0, yhat=yhat, t=t, noise=noise, alphas=alphas, omabs=omabs, alphas_bar_sqrt=alphas_bar_sqrt,
+                  y_t=y_t, y_t_rng=y_t_rng, y0_reparam=y0r, extract=ext)
+    save(name, dict(kind="aux", F=F, H=H, Dx=Dx, C=C, T=T, B=B, rng_seed=133), **arrays)
+
+
 FIXTURES = {
+    "aux": aux_fixture,
+    "stats": stats_fixture,
     "schedules": schedules_fixture,
     "layout": layout_fixture,
     # members trained with the reference objective: y_0 = O(1), absolute 1e-4 bar meaningful
@@ -260,11 +376,6 @@ FIXTURES = {
                                  sd_seed=51, in_seed=52, noise_seed=53, store_inputs=True),
     "c3": lambda: chain_fixture("c3_f96_t40", F=96, H=32, Dx=48, C=3, T=40, B=33, sd_seed=61, in_seed=62,
                                 noise_seed=63),
-    # 'trained-like' scale: lin4 shrunk so eps, y_0 = O(1) and an absolute 1e-4 bar is meaningful
-    "trained": lambda: chain_fixture("trainedlike_f128_t1000", F=128, H=64, Dx=256, C=2, T=1000, B=64,
-                                     sd_seed=71, in_seed=72, noise_seed=73, eps_gain=0.02, keep=[0, 500, 1000]),
-    "trained_tc": lambda: chain_fixture("trainedlike_f256_t1000", F=256, H=64, Dx=128, C=2, T=1000, B=64,
-                                        sd_seed=75, in_seed=76, noise_seed=77, eps_gain=0.02, keep=[0, 500, 1000]),
     # other schedule kind
     "cosine": lambda: chain_fixture("cosine_f64_t60", F=64, H=32, Dx=48, C=2, T=60, B=16, sd_seed=81,
                                     in_seed=82, noise_seed=83, sched="cosine"),
@@ -276,9 +387,9 @@ FIXTURES = {
     # shipped trunk width with a tiny encoder, full T=1000 (reference code, ~1 min)
     "f4096": lambda: chain_fixture("trunk_f4096_t1000", F=4096, H=32, Dx=64, C=2, T=1000, B=64, sd_seed=101,
                                    in_seed=102, noise_seed=103, keep=[0, 1, 500, 999, 1000]),
-    "f4096_trained": lambda: chain_fixture("trunk_f4096_t1000_trainedlike", F=4096, H=32, Dx=64, C=2, T=1000,
-                                           B=64, sd_seed=111, in_seed=112, noise_seed=113, eps_gain=0.02,
-                                           keep=[0, 500, 1000]),
+    # shipped trunk width, TRAINED small tensors on frozen seeded square layers: y_0 = O(1) at F=4096, T=1000
+    "f4096_trained": lambda: trained_fixture("trained_f4096_t1000", F=4096, H=32, Dx=32, C=2, T=1000, B=64, seed=700,
+                                             train_steps=600, frozen_big=True, keep=[0, 1, 500, 999, 1000]),
     # full shipped dims, explicit steps
     "shipped": lambda: shipped_dims_fixture("shipped_dims_steps"),
 }

@@ -53,6 +53,13 @@ class ChainFixture(Fixture):
         m = self.meta
         if m["stored_inputs"]:
             sd = {k[3:]: v for k, v in self.arrays.items() if k.startswith("sd/")}
+            if m.get("sd_overlay"):
+                # the big tensors (W2, W3, gamma tables) are the seeded ones; the trained small ones are stored
+                base = orc.synth_state_dict(m["sd_seed"], m["F"], m["H"], m["Dx"], m["C"], m["T"])
+                base.update(sd)
+                sd = base
+                if check:
+                    assert _digest(*[sd[k].float() for k in sorted(sd)]) == m["sd_digest"], "member drifted"
             x, yhat, noise = self["x"], self["yhat"], self["noise"]
         else:
             sd = orc.synth_state_dict(m["sd_seed"], m["F"], m["H"], m["Dx"], m["C"], m["T"],

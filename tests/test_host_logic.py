@@ -255,6 +255,77 @@ def test_statistics_match_restated_reference():
     assert float(stats.compute_accuracy(mv, label)) == pytest.approx(float((mv == label).float().mean()))
 
 
+# ------------------------------------------------------------------ statistics vs the REFERENCE's own functions
+def _stats_cases():
+    from tests.golden_util import Fixture
+
+    fx = Fixture("stats_reference")
+    return fx, [c["tag"] for c in fx.meta["cases"]]
+
+
+@pytest.mark.parametrize("tag", _stats_cases()[1])
+def test_statistics_match_reference_functions(tag):
+    """stats.py vs outputs of the reference's own majority_voting_for_mc_samples / compute_mean_piws_for_class /
+    calculate_variances / convert_to_prob / compute_ensemble_confidence (classification_train_separately.py:51-68,
+    :102-140, :143-174, :392-398, :425-447), lifted with ``ast`` and executed by tests/golden/make_golden.py::stats_fixture
+    -- incl. vote ties, classes nobody predicts, a single chain.  (ECE is NOT here: torchmetrics is absent, see
+    test_ece_known_answer_parity_unpinned.)"""
+    fx, _ = _stats_cases()
+    case = next(c for c in fx.meta["cases"] if c["tag"] == tag)
+    samples, label = fx[f"{tag}/samples"], fx[f"{tag}/label"]
+    mv = stats.majority_voting_for_mc_samples(samples)
+    assert torch.equal(mv, fx[f"{tag}/mv"])
+    assert torch.equal(stats.majority_voting_for_mc_samples([s for s in samples]), fx[f"{tag}/mv"])
+    assert torch.equal(orc.majority_vote(samples), fx[f"{tag}/mv"])
+    assert torch.allclose(stats.convert_to_prob(samples, case["temperature"]), fx[f"{tag}/prob"], atol=1e-7)
+    assert torch.allclose(stats.compute_ensemble_confidence(samples, case["temperature"]), fx[f"{tag}/conf"], atol=1e-6)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")   # var() of a single chain warns (and is NaN) in the reference too
+        piw = stats.compute_mean_piws_for_class(samples, mv, label)
+        var = stats.calculate_variances(samples, mv, label)
+    for mine, ref in zip(piw, (fx[f"{tag}/piw_correct"], fx[f"{tag}/piw_incorrect"])):
+        assert mine.shape == ref.shape and torch.allclose(mine, ref, atol=1e-6, equal_nan=True), (tag, mine, ref)
+    for mine, ref in zip(var, (fx[f"{tag}/var_correct"], fx[f"{tag}/var_incorrect"])):
+        assert mine.shape == ref.shape and torch.allclose(mine, ref, atol=1e-6, equal_nan=True), (tag, mine, ref)
+    # the oracle's restatements are pinned by the same fixture
+    for mine, ref in zip(orc.mean_piw_per_class(samples, mv, label), (fx[f"{tag}/piw_correct"], fx[f"{tag}/piw_incorrect"])):
+        assert torch.allclose(mine, ref, atol=1e-6, equal_nan=True)
+
+
+def test_q_sample_y0_reparam_extract_match_reference():
+    """diffusion_utils.q_sample / y_0_reparam / extract (a7, a8, a3) with per-row timesteps vs the reference's own
+    outputs (tests/golden/aux_qsample_y0reparam.npz), plus the oracle's restatements."""
+    from tests.golden_util import Fixture
+
+    from nested_diffusion_b200 import diffusion_utils as du
+
+    fx = Fixture("aux_qsample_y0reparam")
+    m = fx.meta
+    sd = {k[3:]: v for k, v in fx.arrays.items() if k.startswith("sd/")}
+    cfg = argparse.Namespace(diffusion=argparse.Namespace(timesteps=m["T"]),
+                             data=argparse.Namespace(num_classes=m["C"], dataset="ChestXRay"),
+                             model=argparse.Namespace(data_dim=m["Dx"], arch="linear", feature_dim=m["F"], hidden_dim=m["H"]))
+    model = nd.ConditionalModel(cfg, guidance=True)
+    model.load_state_dict(sd)
+    model.eval()
+    t = fx["t"]
+    y_t = du.q_sample(fx["y0"], fx["yhat"], fx["alphas_bar_sqrt"], fx["omabs"], t, noise=fx["noise"])
+    assert torch.equal(y_t, fx["y_t"])
+    torch.manual_seed(m["rng_seed"])
+    assert torch.equal(du.q_sample(fx["y0"], fx["yhat"], fx["alphas_bar_sqrt"], fx["omabs"], t), fx["y_t_rng"])
+    assert torch.equal(du.extract(fx["omabs"], t, y_t), fx["extract"])
+    with torch.no_grad():
+        y0r = du.y_0_reparam(model, fx["x"], fx["y_t"], fx["yhat"], fx["yhat"], t, fx["omabs"])
+    assert torch.allclose(y0r, fx["y0_reparam"], rtol=1e-6, atol=1e-6)
+    assert not y0r.requires_grad
+    assert torch.equal(orc.q_sample(fx["y0"], fx["yhat"], fx["alphas_bar_sqrt"], fx["omabs"], t, fx["noise"]), fx["y_t"])
+    with torch.no_grad():
+        eps_fn = orc._Eps(sd, fx["x"], hoist=False)
+        y0o = orc.y_0_reparam(eps_fn, fx["y_t"], fx["yhat"], fx["yhat"], t, fx["omabs"])
+    assert torch.allclose(y0o, fx["y0_reparam"], rtol=1e-6, atol=1e-6)
+
+
 def test_majority_vote_ties_go_to_smallest_label():
     # 4 chains, 2 vote class 1 and 2 vote class 0 -> the reference returns 0 (sorted unique + first argmax)
     s = torch.tensor([[[0.0, 1.0]], [[0.0, 1.0]], [[1.0, 0.0]], [[1.0, 0.0]]])
@@ -265,7 +336,9 @@ def test_majority_vote_ties_go_to_smallest_label():
     assert int(stats.majority_voting_for_mc_samples(s3)[0]) == 2
 
 
-def test_ece_known_answer():
+def test_ece_known_answer_parity_unpinned():
+    """ECE restated from torchmetrics 0.11.4 MulticlassCalibrationError(n_bins=10, norm='l1'); torchmetrics is not in
+    the image, so this one statistic has only a hand-computed known answer: PARITY UNPINNED."""
     probs = torch.tensor([[0.9, 0.1], [0.8, 0.2], [0.4, 0.6], [0.55, 0.45]])
     target = torch.tensor([0, 1, 1, 0])
     # bins (0.5,0.6]: conf .55 acc 1 -> wait .6 falls in (0.5,0.6]: two items conf (.6,.55) acc (1,1);
