@@ -159,7 +159,6 @@ uint64_t ladine_workspace_bytes(const ladine_handle* h);
  *       when the rows pad well and slim tiles when the call is so small that twice as many tiles still fit the
  *       SMs in one round; all geometries give bit-identical results;
  *   "pair_gain_permille": measured per-tile speed ratio pair/single used by the auto choice (default 1080);
- *   "pdl" (0 default | 1): programmatic dependent launch, applied to single-CTA chains only;
  *   "fuse" (0 default | 1): run the tail + head of each reverse step inside the layer-3 GEMM kernel (helper warps
  *       gated by per-row-group arrival counters) instead of a separate kernel; bitwise identical results;
  *   "order" (0 auto | 1 | 2): GEMM tile order -- N-tile-major (a W tile stays hot while a member's rows stream past
@@ -195,6 +194,35 @@ int ladine_debug_layer(ladine_handle* h, const ladine_member* member, int layer,
  * info_out[4] = {units_used, stride, rows_pad, row tiles per member}. */
 int64_t ladine_debug_plan(int32_t K, int32_t rows, int32_t feature_dim_padded, int32_t geometry, int32_t row_major,
                           int32_t units, int32_t* table_out, int64_t cap, int32_t info_out[4]);
+/*
+ * Step-invariant encoder prologue  xf = norm(encoder_x(x))  of the 'linear' ConditionalModel encoder
+ * (latent_model.py:126-135: Linear(data_dim, hidden) BN Softplus Linear(hidden, hidden) BN Softplus Linear(hidden, feature);
+ * :155 norm = BatchNorm1d(feature); applied at :170-171 inside every denoiser call although it does not depend on t).
+ * FP32-grade on the tensor cores (split FP16 operands, error-corrected accumulation).  Pointers of the descriptor are
+ * the module's parameter tensors (state_dict keys encoder_x.{0,3,6}.{weight,bias}, encoder_x.{1,4}.* and norm.*);
+ * the library keeps its own re-laid-out copies (2 x FP16 per weight: as many bytes as the FP32 original).
+ */
+typedef struct ladine_encoder ladine_encoder;
+typedef struct {
+  uint32_t struct_size;            /* sizeof(ladine_encoder_desc) */
+  int32_t data_dim, hidden_dim, feature_dim;
+  float bn_eps;                    /* nn.BatchNorm1d eps (1e-5) */
+  const float* lin_w[3];           /* encoder_x.0 / .3 / .6 .weight : [hidden, data_dim], [hidden, hidden], [feature, hidden] */
+  const float* lin_b[3];           /* ... .bias */
+  const float* bn_w[3];            /* encoder_x.1 / encoder_x.4 / norm .weight */
+  const float* bn_b[3];            /* ... .bias */
+  const float* bn_mean[3];         /* ... .running_mean */
+  const float* bn_var[3];          /* ... .running_var */
+} ladine_encoder_desc;
+int ladine_pack_encoder(ladine_handle* h, const ladine_encoder_desc* desc, void* stream, ladine_encoder** out);
+int ladine_free_encoder(ladine_handle* h, ladine_encoder* enc);   /* synchronises the device */
+uint64_t ladine_encoder_bytes(const ladine_encoder* enc);
+/* xf_out[k] = norm(encoder_x_k(x)) for K encoders on the same images: x [N, data_dim] FP32, xf_out [K, N, feature_dim]
+ * FP32, both device pointers; enqueued on `stream`.  The images are split into FP16 hi + lo operands once for all K. */
+int ladine_encode(ladine_handle* h, const ladine_encoder* const* encoders, int32_t K, const float* x, int32_t N,
+                  float* xf_out, void* stream);
+int64_t ladine_last_encoder_launches(const ladine_handle* h);
+
 /* padded feature dim and padded class count used by the packed layout */
 int ladine_member_fpad(const ladine_member* m);
 int ladine_member_cpad(const ladine_member* m);

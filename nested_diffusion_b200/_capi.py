@@ -42,6 +42,15 @@ class SampleArgs(C.Structure):
     ]
 
 
+class EncoderDesc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("data_dim", C.c_int32), ("hidden_dim", C.c_int32), ("feature_dim", C.c_int32),
+        ("bn_eps", C.c_float),
+        ("lin_w", C.c_void_p * 3), ("lin_b", C.c_void_p * 3), ("bn_w", C.c_void_p * 3), ("bn_b", C.c_void_p * 3),
+        ("bn_mean", C.c_void_p * 3), ("bn_var", C.c_void_p * 3),
+    ]
+
+
 # every symbol include/ladine.h declares: (restype, argtypes)
 SYMBOLS = {
     "ladine_version": (C.c_int, []),
@@ -61,6 +70,12 @@ SYMBOLS = {
     "ladine_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "ladine_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "ladine_get_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
+    "ladine_pack_encoder": (C.c_int, [C.c_void_p, C.POINTER(EncoderDesc), C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ladine_free_encoder": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ladine_encoder_bytes": (C.c_uint64, [C.c_void_p]),
+    "ladine_encode": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                C.c_void_p]),
+    "ladine_last_encoder_launches": (C.c_int64, [C.c_void_p]),
     "ladine_debug_plan": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int32)]),
     "ladine_debug_layer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,

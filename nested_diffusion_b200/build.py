@@ -7,8 +7,8 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", f) for f in ("ladine_api.cu", "ladine_resident.cu", "ladine_tensor.cu")]
-HDR = [os.path.join(HERE, "csrc", f) for f in ("ladine_common.cuh", "ladine_internal.cuh")] + [
+SRC = [os.path.join(HERE, "csrc", f) for f in ("ladine_api.cu", "ladine_resident.cu", "ladine_tensor.cu", "ladine_split.cu", "ladine_encoder.cu")]
+HDR = [os.path.join(HERE, "csrc", f) for f in ("ladine_common.cuh", "ladine_internal.cuh", "ladine_tc.cuh", "ladine_tensor.cuh", "ladine_split.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "ladine.h")]
 OUT = os.path.join(HERE, "lib", "libladine.so")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]

@@ -293,9 +293,10 @@ int ladine_destroy(ladine_handle* h) {
   if (!h) return LADINE_ERR_INVALID;
   {
     DeviceGuard g(h->device);
-    if (h->ws) {
+    if (h->ws || h->enc_ws) {
       cudaDeviceSynchronize();
       cudaFree(h->ws);
+      cudaFree(h->enc_ws);
     }
     for (auto& s : h->spans) {
       cudaEventDestroy(s.a);
@@ -386,7 +387,7 @@ int ladine_pack_member(ladine_handle* h, const ladine_member_desc* d, void* stre
     return fail(h, LADINE_ERR_NOMEM, "device allocation failed while packing a member");
   }
 
-  const float gain = tensor ? kLog2e : 1.0f;
+  const float gain = (tensor && !split) ? kLog2e : 1.0f;   // FP32X keeps natural units (exact-semantics softplus)
   const float* lin_b[3] = {d->lin1_b, d->lin2_b, d->lin3_b};
   const size_t tf = (size_t)T * Fp;
   if (split) {
@@ -633,10 +634,6 @@ int ladine_set_option(ladine_handle* h, const char* key, int64_t value) {
     h->fuse = value != 0;
     return LADINE_OK;
   }
-  if (strcmp(key, "pdl") == 0) {
-    h->pdl = value != 0;
-    return LADINE_OK;
-  }
   if (strcmp(key, "ctas") == 0) {
     if (value < 0 || value > 3) return fail(h, LADINE_ERR_INVALID, "ctas must be 0 (auto), 1, 2 or 3 (slim tiles)");
     h->ctas = (int)value;
@@ -747,8 +744,7 @@ int ladine_debug_layer(ladine_handle* h, const ladine_member* member, int layer,
   if (!h) return LADINE_ERR_INVALID;
   if (!member || !h_in || rows < 1 || (layer != 2 && layer != 3) || t < 0 || t >= member->T)
     return fail(h, LADINE_ERR_INVALID, "bad debug-layer arguments");
-  if (member->precision == LADINE_PREC_FP32 || member->split)
-    return fail(h, LADINE_ERR_UNSUPPORTED, "debug layer is for the FP16 / BF16 tensor path");
+  if (member->precision == LADINE_PREC_FP32) return fail(h, LADINE_ERR_UNSUPPORTED, "debug layer is for the tensor path");
   if ((layer == 2 && !h_out) || (layer == 3 && !part)) return fail(h, LADINE_ERR_INVALID, "missing output buffer");
   DeviceGuard guard(h->device);
   int rc = ensure_workspace(h, sched_bytes_bound(1, rows, member->Fp / 128));

@@ -46,6 +46,10 @@ struct ladine_handle {
   // grow-only workspace
   void* ws = nullptr;
   uint64_t ws_bytes = 0;
+  // grow-only workspace of the encoder prologue (ladine_encode)
+  void* enc_ws = nullptr;
+  uint64_t enc_ws_bytes = 0;
+  int64_t last_encoder_launches = 0;
   // driver entry point for tensor-map encoding (resolved lazily through the runtime)
   void* encode_tiled = nullptr;
   // optional per-kernel event timing (tensor path)
@@ -56,7 +60,6 @@ struct ladine_handle {
   // Bitwise identical to the separate tail/head kernel; measured 1-3 % SLOWER at config 2 (the helpers compete with
   // the SMEM-port-bound mainloop and the last row groups drain after the last MMA), so it is opt-in.
   bool fuse = false;
-  bool pdl = false;         // programmatic dependent launch: opt-in, single-CTA chains only (see ladine_tensor.cu)
   int ctas = 0;             // 0 = choose per call, 1 = cta_group::1, 2 = cta_group::2 CTA pairs
   int order = 0;             // GEMM tile order: 0 = auto, 1 = N-tile-major, 2 = row-major
   int tail_vec = 0;          // tail/head features per thread: 0 = pick by wave quantisation, else 4 or 8

@@ -24,14 +24,12 @@
 #include <cstdio>
 
 #include "ladine_internal.cuh"
+#include "ladine_tc.cuh"
+#include "ladine_tensor.cuh"
 
 namespace ladine {
 namespace {
 
-constexpr int BM = 128;   // rows per tile  (UMMA M)
-constexpr int BN = 256;   // cols per tile  (UMMA N)
-constexpr int BK = 64;    // K per stage    (64 x 2 B = one 128-byte swizzle row)
-constexpr int UK = 16;    // K per tcgen05.mma (kind::f16)
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * BN;  // 512
 constexpr int kGemmThreads = 320;
@@ -48,178 +46,8 @@ constexpr int kMmaWarp = 9;
 constexpr size_t kRowMajorActBytes = (size_t)32 << 20;
 
 // ------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      printf("ladine: mbarrier timeout role=%d block=%d thread=%d bar=%u parity=%u\n", who, (int)blockIdx.x,
-             (int)threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major; issued by ONE thread
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on an mbarrier once every tcgen05 op issued so far by this thread has completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128-byte-swizzled shared-memory operand descriptor (PTX ISA "tcgen05 shared memory
-// descriptor"): start address >> 4 in bits [0,14); leading byte offset (unused for swizzled K-major,
-// encoded 1) in [16,30); stride byte offset = 8 rows x 128 B = 1024 B (>>4 = 64) in [32,46);
-// descriptor version 1 in [46,48); layout type 2 = SWIZZLE_128B in [61,64).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-
-// ------------------------------------------------------------------------------------------
 // GEMM + fused epilogue
 // ------------------------------------------------------------------------------------------
-enum TailMode { kInit = 0, kMid = 1, kFinal = 2 };
-
-struct TailHeadParams {
-  const float* A1[LADINE_MAX_GROUP];   // row of the NEXT step (t-1), x log2e
-  const float* C1[LADINE_MAX_GROUP];
-  const float* W1y[LADINE_MAX_GROUP];  // [Fp, Cp]
-  const float* b4[LADINE_MAX_GROUP];
-  const float* part;   // [M_total, NB, Cp]
-  const float* y_prev; // [M_total, Cp]  chain state before this step (ping-pong: column-split CTAs all read it)
-  float* y_next;       // [M_total, Cp]  chain state after this step (written by column split 0)
-  const float* xf;     // [K, N, Fin]
-  const float* u;      // [K, N, Fp]
-  const float* ytmean; // [K, N, C]
-  const float* y_init; // [K, D, N, C] or null (kInit only)
-  const float* noise;  // [K, D, S, N, C] or null
-  void* h1;            // [M_total, Fp] 16-bit
-  float* y_out;        // kFinal / last step
-  float* traj_out;
-  float* prob_out;
-  float temperature;
-  StepCoef coef;       // coefficients of the step being finished (unused for kInit)
-  uint64_t seed;
-  ChainIds ids;
-  int t;               // table index of the step being finished (kInit: unused)
-  int slot;            // noise slot / trajectory entry consumed-written by this launch
-  int traj_entry;
-  int N, D, C, Fin, Fp, NB, rows_pad, n_slots, n_traj, dchunk, write_out, colsplit;
-  int ld_h1;           // row stride of h1 in elements: Fp, or 2 * Fp in split (FP32X) mode
-  int split;           // FP32X: h1 is written as FP16 hi (columns [0, Fp)) + lo (columns [Fp, 2 * Fp)) parts
-};
-
-struct GemmParams {
-  CUtensorMap tmA;                     // activations in  [M_total, Fp] 16-bit, box 64 x 128
-  CUtensorMap tmB[LADINE_MAX_GROUP];   // member weights  [Fp, Fp]      16-bit, box 64 x (256 / CTAS)
-  const float* scale[LADINE_MAX_GROUP];  // A_l[t] row of each member (already offset to row t), x log2e
-  const float* shift[LADINE_MAX_GROUP];  // C_l[t] row, x log2e
-  const float* W4[LADINE_MAX_GROUP];     // [Cp, Fp]  (layer 3 only)
-  void* h_out;                         // layer 2: [M_total, Fp] 16-bit
-  float* part;                         // layer 3: [M_total, NB, Cp]
-  int Fp, NB, KB;                      // padded feature dim, N tiles (Fp/256), K blocks (Fp/64)
-  // FP32X (split operands): A = [A_hi | A_lo] and W = [W_hi | W_lo] side by side (row stride 2 * Fp), and the K loop
-  // runs three segments over the same accumulator -- A_lo.W_hi, A_hi.W_lo, A_hi.W_hi (small terms first) -- i.e. a
-  // plain GEMM over an extended K: the pipeline, tile schedule and TMEM protocol are those of the 16-bit path.
-  int nseg;                            // 1, or 3 in split mode
-  int ld_out;                          // row stride of h_out in elements (Fp, or 2 * Fp in split mode)
-  int rows;                            // valid rows per member
-  int rows_pad;                        // row stride between members (multiple of 128 * CTAS)
-  // static tile schedule: unit u (a CTA, or a CTA pair) runs sched[u * sched_stride + 0, 1, ...] until a -1.
-  // entry = member << 23 | nb << 13 | mb << 1 | half   (half: CTA-pair tile of 2 x 64 rows, M=128 MMAs)
-  const int32_t* sched;
-  int sched_stride;
-  uint32_t idesc;                      // full tiles: M = 128 * CTAS
-  uint32_t idesc_half;                 // pair half tiles: M = 128 (64 rows per CTA)
-  // ---- layer 3 with the tail + head fused in (fuse != 0) ----
-  // After a CTA has written its lin4 partials it signals the row group's arrival counter; when all NB column
-  // tiles of the group are in, every one of those CTAs finishes the reverse step for its rows (eps, posterior
-  // update -- recomputed identically by each) and produces h1 of the next step for ITS 256 columns.
-  int fuse;
-  int do_head;                         // 0 on the last step of the chain (no next h1)
-  int mblk_total;                      // row tiles per member (full + half)
-  int* group_arrivals;                 // [K * mblk_total * CTAS], monotonically increasing over the chain
-  int arrivals_target;                 // NB * (layer-3 launches of this chain so far, this one included)
-  TailHeadParams th;
-};
-
-struct TileCode {
-  int member, nb, mb, half;
-  __host__ __device__ static int32_t pack(int member, int nb, int mb, int half) {
-    return (int32_t)((member << 23) | (nb << 13) | (mb << 1) | half);
-  }
-  __device__ explicit TileCode(int32_t c) : member(c >> 23), nb((c >> 13) & 1023), mb((c >> 1) & 4095), half(c & 1) {}
-};
-
 // pipeline geometry per CTA: CTAS = 1 -> A 128x64 + B 256x64 per stage; CTAS = 2 (cta_group::2, the
 // CTA pair computes a 256x256 tile) -> A 128x64 + the CTA's half of B 128x64 per stage, so deeper ring
 // BNT = tile width: 256, or 128 ("slim" single-CTA tiles for calls too small to fill the SMs with 256-wide tiles:
@@ -243,80 +71,6 @@ struct __align__(8) GemmBarriers {
   uint32_t tmem_base;
   int published;   // layer 3, fused: tiles of this CTA whose lin4 partials are out (epilogue -> helper warps)
 };
-
-// 256-bit global store (one full 32-byte sector per thread)
-__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&v)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
-               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
-}
-
-// FP32X: lo parts of two values whose FP16 hi parts are packed in `hi2`: fp16(v - float(hi))
-__device__ __forceinline__ uint32_t split_lo(uint32_t hi2, float v0, float v1) {
-  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
-  return Pack16<__half>::pack(v0 - h.x, v1 - h.y);
-}
-
-// ---- programmatic dependent launch (PDL) ----
-// Every kernel of the chain is launched with programmaticStreamSerialization: its CTAs may start while the
-// previous kernel drains, run their prologue (barrier init, TMEM alloc, descriptor prefetch), and must
-// execute pdl_wait() before touching any global memory the previous kernel wrote (or that it still reads).
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-// ---- cluster / cta_group::2 helpers ----
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  // default semantics (as CUTLASS ClusterBarrier::arrive): an explicit .release.cluster lowers to a GPU-scope
-  // MEMBAR + ERRBAR, which cost ~1 us per arrive when it sat in the per-stage producer loop
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// TMA load of one CTA of a pair; completion bytes are signalled on `bar` (a shared::cluster address, normally
-// the leader CTA's barrier)
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                              uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// commit of the pair's MMAs, delivered to the barrier at the same offset in BOTH CTAs
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      ::"r"(bar), "h"((uint16_t)3)
-      : "memory");
-}
 
 // Finish reverse step th.t for the CTA's rows [row_base, row_base + nrows) of member k and (unless it is the last
 // step) write their h1 of the next step for the 256 columns of N tile nb.  Called by the 128 epilogue threads.
@@ -497,8 +251,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  pdl_launch_dependents();  // the next kernel's CTAs can take this SM the moment this CTA retires
-  pdl_wait();               // everything below reads/writes buffers shared with the previous kernels
 
   const int32_t* my_sched = p.sched + (size_t)unit * p.sched_stride;
 
@@ -515,25 +267,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
         const int arow = tc.member * p.rows_pad + tc.mb * (BM * CTAS) + (int)rank * (tc.half ? BM / 2 : BM);
         const int brow = tc.nb * BNT + (int)rank * Cfg::kBRows;
         const CUtensorMap* tb = &p.tmB[tc.member];
-        for (int seg = 0; seg < p.nseg; ++seg) {
-          // split mode: segment 0 = A_lo . W_hi, 1 = A_hi . W_lo, 2 = A_hi . W_hi; the lo halves start at column Fp
-          const int acol0 = (p.nseg == 3 && seg == 0) ? p.Fp : 0;
-          const int bcol0 = (p.nseg == 3 && seg == 1) ? p.Fp : 0;
-          for (int kb = 0; kb < p.KB; ++kb) {
-            mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u, 0);
-            const uint32_t fb = smem_u32(&bars->full[stage]);
-            if (CTAS == 1) {
-              mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
-              tma_load_2d(smem_u32(sA + stage * Cfg::kABytes), &p.tmA, fb, acol0 + kb * BK, arow);
-              tma_load_2d(smem_u32(sB + stage * Cfg::kBBytes), tb, fb, bcol0 + kb * BK, brow);
-            } else {
-              const uint32_t lfb = mapa_rank(fb, 0);  // both CTAs' bytes complete on the leader's barrier
-              if (rank == 0) mbar_arrive_expect_tx(fb, 2 * Cfg::kStageBytes);
-              tma_load_2d_pair(smem_u32(sA + stage * Cfg::kABytes), &p.tmA, lfb, acol0 + kb * BK, arow);
-              tma_load_2d_pair(smem_u32(sB + stage * Cfg::kBBytes), tb, lfb, bcol0 + kb * BK, brow);
-            }
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        for (int kb = 0; kb < p.KB; ++kb) {
+          mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u, 0);
+          const uint32_t fb = smem_u32(&bars->full[stage]);
+          if (CTAS == 1) {
+            mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+            tma_load_2d(smem_u32(sA + stage * Cfg::kABytes), &p.tmA, fb, kb * BK, arow);
+            tma_load_2d(smem_u32(sB + stage * Cfg::kBBytes), tb, fb, kb * BK, brow);
+          } else {
+            const uint32_t lfb = mapa_rank(fb, 0);  // both CTAs' bytes complete on the leader's barrier
+            if (rank == 0) mbar_arrive_expect_tx(fb, 2 * Cfg::kStageBytes);
+            tma_load_2d_pair(smem_u32(sA + stage * Cfg::kABytes), &p.tmA, lfb, kb * BK, arow);
+            tma_load_2d_pair(smem_u32(sB + stage * Cfg::kBBytes), tb, lfb, kb * BK, brow);
           }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -551,8 +298,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
         mbar_wait(smem_u32(&bars->acc_empty[as]), aphase ^ 1u, 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BNT);
-        const int kblocks = p.KB * p.nseg;   // split mode: three K segments into the same accumulator
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = 0; kb < p.KB; ++kb) {
           mbar_wait(smem_u32(&bars->full[stage]), phase, 2);
           tc_fence_after();
           const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * Cfg::kABytes));
@@ -659,19 +405,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
           if (LAYER == 2) {
             if (valid) {
               // 32 consecutive 16-bit outputs of this row = 64 B = two full 32-byte sectors: 256-bit stores
-              T16* dst = reinterpret_cast<T16*>(p.h_out) + grow * p.ld_out + nb * BNT + ocol;
+              T16* dst = reinterpret_cast<T16*>(p.h_out) + grow * p.Fp + nb * BNT + ocol;
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
                 uint32_t o[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] = Pack16<T16>::pack(hcol[16 * q + 2 * i], hcol[16 * q + 2 * i + 1]);
                 st_global_256(dst + 16 * q, o);
-                if (p.nseg == 3) {   // FP32X: the residual of the FP16 rounding goes to the lo half (warp-uniform branch)
-                  uint32_t ol[8];
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) ol[i] = split_lo(o[i], hcol[16 * q + 2 * i], hcol[16 * q + 2 * i + 1]);
-                  st_global_256(dst + p.Fp + 16 * q, ol);
-                }
               }
             }
           } else {
@@ -794,8 +534,6 @@ __global__ void __launch_bounds__(kTailThreads, (CP <= 4 ? 8 : 1)) tailhead_kern
   const int nd = min(p.dchunk, p.D - d0);
   const int tid = threadIdx.x;
   const int C = p.C;
-  pdl_launch_dependents();
-  pdl_wait();
 
   // ---------------- tail: finish step t for rows (k, n, d0..d0+nd) ----------------
   if (CP != C)
@@ -881,7 +619,9 @@ __global__ void __launch_bounds__(kTailThreads, (CP <= 4 ? 8 : 1)) tailhead_kern
       }
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        xl[j] = ((f0 + j) < p.Fin ? __ldg(xfrow + f0 + j) : 0.f) * kLn2;
+        // 16-bit path: tables are pre-multiplied by log2(e), so softplus = lg2(1 + 2^v2) * ln2 and ln2 rides on xf;
+        // FP32X: natural units and the exact-semantics softplus
+        xl[j] = ((f0 + j) < p.Fin ? __ldg(xfrow + f0 + j) : 0.f) * (p.split ? 1.0f : kLn2);
         q[j] = fmaf(a1[j], uu[j], c1[j]);
 #pragma unroll
         for (int c = 0; c < CP; ++c) pc[j][c] = a1[j] * __ldg(p.W1y[k] + (size_t)(f0 + j) * CP + c);  // padded classes: 0
@@ -898,7 +638,8 @@ __global__ void __launch_bounds__(kTailThreads, (CP <= 4 ? 8 : 1)) tailhead_kern
         float v2 = q[j];
 #pragma unroll
         for (int c = 0; c < CP; ++c) v2 = fmaf(pc[j][c], yv[c], v2);
-        const float t = v2 > kSoftplusThreshold * kLog2e ? v2 : lg2_approx(1.0f + ex2_approx(v2));
+        const float t = p.split ? softplus_precise(v2)
+                                : (v2 > kSoftplusThreshold * kLog2e ? v2 : lg2_approx(1.0f + ex2_approx(v2)));
         hv[j] = t * xl[j];
       }
       if (VEC == 8) {
@@ -935,6 +676,9 @@ __global__ void __launch_bounds__(kTailThreads, (CP <= 4 ? 8 : 1)) tailhead_kern
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+}  // namespace
+
+// ---- tensor-map helpers (external linkage: shared with ladine_split.cu / ladine_encoder.cu) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -973,6 +717,8 @@ bool make_tmap(ladine_handle* h, CUtensorMap* out, const void* base, uint64_t ro
   return true;
 }
 
+namespace {
+
 // instruction descriptor for kind::f16 (PTX ISA "Instruction descriptor"): D format F32 (1) at [4,6);
 // A/B format (0 = F16, 1 = BF16) at [7,10)/[10,13); A,B K-major (0) at 15/16; N>>3 at [17,23); M>>4 at [24,29)
 uint32_t make_idesc(bool bf16, int ctas, int n = BN) {
@@ -980,28 +726,8 @@ uint32_t make_idesc(bool bf16, int ctas, int n = BN) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)((BM * ctas) >> 4) << 24);
 }
 
-// Run `fn` (a cudaFuncSetAttribute call) the first time a kernel instantiation is launched on the current device; `done`
-// is that instantiation's bitmask over device ordinals.
-template <typename Fn>
-cudaError_t configure_once(std::atomic<uint64_t>& done, Fn fn) {
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  const uint64_t bit = dev < 64 ? (uint64_t)1 << dev : 0;
-  if (bit && (done.load(std::memory_order_acquire) & bit)) return cudaSuccess;
-  e = fn();
-  if (e == cudaSuccess && bit) done.fetch_or(bit, std::memory_order_release);
-  return e;
-}
-
-// Programmatic dependent launch is OPT-IN (ladine_set_option("pdl", 1)) and only ever applied to chains of
-// single-CTA kernels: measured neutral on B200 (the chain is bound by the shared-memory port and the power cap,
-// not by launch gaps), and PDL combined with cluster launches (CTA pairs) dead-locked the GPU after a few hundred
-// steps of a 1000-step chain (driver 580.159) -- so a chain that uses pairs never sets the attribute.
-inline bool pdl_allowed(const ladine_handle* h, int ctas) { return h->pdl && ctas == 1; }
-
 template <int LAYER, typename T16, int CP, int CTAS, int BNT = BN>
-cudaError_t launch_gemm_t(const GemmParams& p, int grid, bool pdl, cudaStream_t st) {
+cudaError_t launch_gemm_t(const GemmParams& p, int grid, cudaStream_t st) {
   const size_t smem = tensor_gemm_smem_bytes(CP);
   auto kern = trunk_gemm_kernel<LAYER, T16, CP, CTAS, BNT>;
   // once per (kernel instantiation, device): the call costs several microseconds of host time, which a chain of
@@ -1016,11 +742,8 @@ cudaError_t launch_gemm_t(const GemmParams& p, int grid, bool pdl, cudaStream_t 
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   int na = 0;
-  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[na].val.programmaticStreamSerializationAllowed = (pdl && CTAS == 1) ? 1 : 0;
-  ++na;
   if (CTAS == 2) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = 2;
@@ -1037,15 +760,15 @@ cudaError_t launch_gemm_t(const GemmParams& p, int grid, bool pdl, cudaStream_t 
 constexpr int kGeomSlim = 3;
 
 template <int LAYER, typename T16>
-cudaError_t launch_gemm_c(const GemmParams& p, int grid, int Cp, int ctas, bool pdl, cudaStream_t st) {
+cudaError_t launch_gemm_c(const GemmParams& p, int grid, int Cp, int ctas, cudaStream_t st) {
   if (LAYER == 2) {  // the layer-2 epilogue does not depend on the class count
-    if (ctas == kGeomSlim) return launch_gemm_t<2, T16, 2, 1, 128>(p, grid, pdl, st);
-    return ctas == 2 ? launch_gemm_t<2, T16, 2, 2>(p, grid, pdl, st) : launch_gemm_t<2, T16, 2, 1>(p, grid, pdl, st);
+    if (ctas == kGeomSlim) return launch_gemm_t<2, T16, 2, 1, 128>(p, grid, st);
+    return ctas == 2 ? launch_gemm_t<2, T16, 2, 2>(p, grid, st) : launch_gemm_t<2, T16, 2, 1>(p, grid, st);
   }
 #define LADINE_GEMM_CASE(CPV)                                                                          \
   case CPV:                                                                                            \
-    if (ctas == kGeomSlim) return launch_gemm_t<3, T16, CPV, 1, 128>(p, grid, pdl, st);                \
-    return ctas == 2 ? launch_gemm_t<3, T16, CPV, 2>(p, grid, pdl, st) : launch_gemm_t<3, T16, CPV, 1>(p, grid, pdl, st);
+    if (ctas == kGeomSlim) return launch_gemm_t<3, T16, CPV, 1, 128>(p, grid, st);                \
+    return ctas == 2 ? launch_gemm_t<3, T16, CPV, 2>(p, grid, st) : launch_gemm_t<3, T16, CPV, 1>(p, grid, st);
   switch (Cp) {
     LADINE_GEMM_CASE(2)
     LADINE_GEMM_CASE(4)
@@ -1057,13 +780,13 @@ cudaError_t launch_gemm_c(const GemmParams& p, int grid, int Cp, int ctas, bool 
 }
 
 template <int LAYER>
-cudaError_t launch_gemm(const GemmParams& p, int grid, bool bf16, int Cp, int ctas, bool pdl, cudaStream_t st) {
-  return bf16 ? launch_gemm_c<LAYER, __nv_bfloat16>(p, grid, Cp, ctas, pdl, st)
-              : launch_gemm_c<LAYER, __half>(p, grid, Cp, ctas, pdl, st);
+cudaError_t launch_gemm(const GemmParams& p, int grid, bool bf16, int Cp, int ctas, cudaStream_t st) {
+  return bf16 ? launch_gemm_c<LAYER, __nv_bfloat16>(p, grid, Cp, ctas, st)
+              : launch_gemm_c<LAYER, __half>(p, grid, Cp, ctas, st);
 }
 
 template <int MODE, typename T16, int CP, int VEC>
-cudaError_t launch_tail_t(const TailHeadParams& p, dim3 grid, bool pdl, cudaStream_t st) {
+cudaError_t launch_tail_t(const TailHeadParams& p, dim3 grid, cudaStream_t st) {
   auto kern = tailhead_kernel<MODE, T16, CP, VEC>;
   // same shared-memory carveout as the GEMM kernels, so the SMs are not reconfigured at every kernel boundary
   static std::atomic<uint64_t> configured{0};
@@ -1076,23 +799,20 @@ cudaError_t launch_tail_t(const TailHeadParams& p, dim3 grid, bool pdl, cudaStre
   cfg.blockDim = dim3(kTailThreads);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.attrs = nullptr;
+  cfg.numAttrs = 0;
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 template <int MODE>
-cudaError_t launch_tail(const TailHeadParams& p, dim3 grid, bool bf16, int Cp, int vec, bool pdl, cudaStream_t st) {
+cudaError_t launch_tail(const TailHeadParams& p, dim3 grid, bool bf16, int Cp, int vec, cudaStream_t st) {
 #define LADINE_TAIL_CASE(CPV)                                                                                     \
   case CPV:                                                                                                       \
     if (vec == 4)                                                                                                 \
-      return bf16 ? launch_tail_t<MODE, __nv_bfloat16, CPV, 4>(p, grid, pdl, st)                                  \
-                  : launch_tail_t<MODE, __half, CPV, 4>(p, grid, pdl, st);                                        \
-    return bf16 ? launch_tail_t<MODE, __nv_bfloat16, CPV, 8>(p, grid, pdl, st)                                    \
-                : launch_tail_t<MODE, __half, CPV, 8>(p, grid, pdl, st);
+      return bf16 ? launch_tail_t<MODE, __nv_bfloat16, CPV, 4>(p, grid, st)                                  \
+                  : launch_tail_t<MODE, __half, CPV, 4>(p, grid, st);                                        \
+    return bf16 ? launch_tail_t<MODE, __nv_bfloat16, CPV, 8>(p, grid, st)                                    \
+                : launch_tail_t<MODE, __half, CPV, 8>(p, grid, st);
   switch (Cp) {
     LADINE_TAIL_CASE(2)
     LADINE_TAIL_CASE(4)
@@ -1267,7 +987,7 @@ struct TensorChain {
   TailHeadParams tp{};
   dim3 tgrid;
   int grid = 0, K = 0, Fp = 0, Cp = 0, slot_base = 0, ctas = 1, ycur = 0, g3_launches = 0, tail_vec = 8;
-  bool pdl = false, fuse = false;
+  bool fuse = false, split = false;
   float* ybuf[2] = {nullptr, nullptr};
   bool bf16 = false;
 
@@ -1288,16 +1008,15 @@ struct TensorChain {
     st = st_;
     const ladine_member* m0 = members[0];
     bf16 = m0->precision == LADINE_PREC_BF16;
-    const bool split = m0->split != 0;
+    split = m0->split != 0;
     Fp = m0->Fp;
     Cp = m0->Cp;
     K = a.K;
     const int rows = a.N * a.D;
-    ctas = choose_ctas(h, K, rows, Fp);
+    ctas = split ? kGeomSlim : choose_ctas(h, K, rows, Fp);   // FP32X: 128 x 128 tiles (ladine_split.cu)
     const bool slim = ctas == kGeomSlim;
     const int cpu = slim ? 1 : ctas;            // CTAs per scheduling unit (2 for pairs)
     const int bnt = slim ? 128 : BN;            // tile width
-    pdl = pdl_allowed(h, cpu);
     // the fused tail + head spins on other CTAs of the same launch: every CTA must be resident, so it is only
     // used when this chain is the sole lane, and its extra per-column parameters fit in smem up to 8 classes
     fuse = h->fuse && single_lane && Cp <= 8 && !slim && !split;
@@ -1337,8 +1056,6 @@ struct TensorChain {
       g3.W4[k] = members[k]->W4;
     }
     for (GemmParams* g : {&g2, &g3}) {
-      g->nseg = split ? 3 : 1;
-      g->ld_out = (int)ld;
       g->Fp = Fp;
       g->NB = Fp / BN;   // 256-column groups: the lin4 partial buffer has 2 * NB slots per row whatever the tile width
       g->KB = Fp / BK;
@@ -1420,7 +1137,7 @@ struct TensorChain {
     tp.y_prev = ybuf[ycur];
     tp.y_next = ybuf[ycur ^ 1];
     ycur ^= 1;
-    e = launch_tail<kInit>(tp, tgrid, bf16, Cp, tail_vec, pdl, st);
+    e = launch_tail<kInit>(tp, tgrid, bf16, Cp, tail_vec, st);
     if (e == cudaSuccess) ++*launches;
     return e;
   }
@@ -1436,7 +1153,7 @@ struct TensorChain {
     cudaError_t e;
     {
       ProfSpan ps(h, st, 0);
-      e = launch_gemm<2>(g2, grid, bf16, Cp, ctas, pdl, st);
+      e = split ? launch_split_gemm(2, g2, grid, Cp, st) : launch_gemm<2>(g2, grid, bf16, Cp, ctas, st);
     }
     if (e != cudaSuccess) return e;
     tp.coef = h_coef[t];
@@ -1455,20 +1172,20 @@ struct TensorChain {
       g3.arrivals_target = (Fp / BN) * (++g3_launches);
       {
         ProfSpan ps(h, st, 1);
-        e = launch_gemm<3>(g3, grid, bf16, Cp, ctas, pdl, st);
+        e = launch_gemm<3>(g3, grid, bf16, Cp, ctas, st);
       }
       if (e == cudaSuccess) *launches += 2;
       return e;
     }
     {
       ProfSpan ps(h, st, 1);
-      e = launch_gemm<3>(g3, grid, bf16, Cp, ctas, pdl, st);
+      e = split ? launch_split_gemm(3, g3, grid, Cp, st) : launch_gemm<3>(g3, grid, bf16, Cp, ctas, st);
     }
     if (e != cudaSuccess) return e;
     {
       ProfSpan ps(h, st, 2);
-      e = last ? launch_tail<kFinal>(tp, tgrid, bf16, Cp, tail_vec, pdl, st)
-               : launch_tail<kMid>(tp, tgrid, bf16, Cp, tail_vec, pdl, st);
+      e = last ? launch_tail<kFinal>(tp, tgrid, bf16, Cp, tail_vec, st)
+               : launch_tail<kMid>(tp, tgrid, bf16, Cp, tail_vec, st);
     }
     if (e == cudaSuccess) *launches += 3;
     return e;
@@ -1511,23 +1228,22 @@ cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int lay
   if (e != cudaSuccess) return e;
   const int Fp = m->Fp;
   // debug entry: "ctas" = 2 exercises the CTA-pair geometry (incl. half tiles), 3 the slim 128-wide tiles
-  const bool slim = h->ctas == kGeomSlim;
-  const int ctas = (h->ctas == 2) ? 2 : 1;
+  const bool slim = h->ctas == kGeomSlim || m->split;   // FP32X always runs 128 x 128 tiles
+  const int ctas = (h->ctas == 2 && !m->split) ? 2 : 1;
   const int bnt = slim ? 128 : BN;
   const TilePlan plan = plan_tiles(1, rows, Fp / bnt, ctas, h->sm_count / ctas);
   e = cudaMemcpyAsync(sched_buf, plan.table.data(), plan.table.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return e;
   GemmParams g{};
-  if (!make_tmap(h, &g.tmA, h_in, (uint64_t)plan.rows_pad, Fp, BM, bf16, err)) return cudaErrorInvalidValue;
-  if (!make_tmap(h, &g.tmB[0], layer == 2 ? m->W2h : m->W3h, Fp, Fp, bnt / ctas, bf16, err)) return cudaErrorInvalidValue;
+  const uint64_t ld = (uint64_t)Fp * (m->split ? 2 : 1);   // FP32X: h_in / h_out rows are [hi | lo]
+  if (!make_tmap(h, &g.tmA, h_in, (uint64_t)plan.rows_pad, ld, BM, bf16, err)) return cudaErrorInvalidValue;
+  if (!make_tmap(h, &g.tmB[0], layer == 2 ? m->W2h : m->W3h, Fp, ld, bnt / ctas, bf16, err)) return cudaErrorInvalidValue;
   g.scale[0] = m->A[layer - 1] + (size_t)t * Fp;
   g.shift[0] = m->Cc[layer - 1] + (size_t)t * Fp;
   g.W4[0] = m->W4;
   g.h_out = h_out;
   g.part = part;
   g.Fp = Fp;
-  g.nseg = 1;
-  g.ld_out = Fp;
   g.NB = Fp / BN;
   g.KB = Fp / BK;
   g.rows = rows;
@@ -1538,8 +1254,9 @@ cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int lay
   g.idesc_half = make_idesc(bf16, 1);
   const int grid = plan.units * ctas;
   const int geom = slim ? kGeomSlim : ctas;
-  return layer == 2 ? launch_gemm<2>(g, grid, bf16, m->Cp, geom, false, st)
-                    : launch_gemm<3>(g, grid, bf16, m->Cp, geom, false, st);
+  if (m->split) return launch_split_gemm(layer, g, grid, m->Cp, st);
+  return layer == 2 ? launch_gemm<2>(g, grid, bf16, m->Cp, geom, st)
+                    : launch_gemm<3>(g, grid, bf16, m->Cp, geom, st);
 }
 
 }  // namespace ladine

@@ -174,11 +174,131 @@ def split_tf32_linear(x: torch.Tensor, lin: torch.nn.Linear) -> torch.Tensor:
     return out if lin.bias is None else out + lin.bias
 
 
-def encode_features(model, x: torch.Tensor, mode: str = "fp32") -> torch.Tensor:
-    """``norm(encoder_x(x))`` in PyTorch (step-invariant; latent_model.py:170-171).
+# ------------------------------------------------------------------------------------------------
+# encoder prologue on libladine (ladine_encode): FP32-grade split-operand tcgen05 GEMMs, SURVEY.md §8f-3
+# ------------------------------------------------------------------------------------------------
+def _kernel_encoder_layers(model):
+    """The (Linear, BN, Linear, BN, Linear, norm) modules of a 'linear'-arch encoder the kernel can run, else None."""
+    nn = torch.nn
+    enc, norm = getattr(model, "encoder_x", None), getattr(model, "norm", None)
+    if not (isinstance(enc, nn.Sequential) and len(enc) == 7 and isinstance(norm, nn.BatchNorm1d)):
+        return None
+    l0, b1, a2, l3, b4, a5, l6 = list(enc)
+    if not (isinstance(l0, nn.Linear) and isinstance(l3, nn.Linear) and isinstance(l6, nn.Linear)
+            and isinstance(b1, nn.BatchNorm1d) and isinstance(b4, nn.BatchNorm1d)
+            and isinstance(a2, nn.Softplus) and isinstance(a5, nn.Softplus)):
+        return None
+    if any(a.beta != 1 or a.threshold != 20 for a in (a2, a5)):
+        return None
+    if l0.bias is None or l3.bias is None or l6.bias is None or not all(b.affine and b.track_running_stats for b in (b1, b4, norm)):
+        return None
+    if not (b1.eps == b4.eps == norm.eps) or l0.weight.dtype != torch.float32 or not l0.weight.is_cuda:
+        return None
+    if not (l0.out_features == l3.in_features == l3.out_features == l6.in_features and l6.out_features == norm.num_features):
+        return None
+    return (l0, l3, l6), (b1, b4, norm)
 
-    mode "fp32" (default): the module as is.  "tf32x3": on CUDA, an MLP encoder whose first Linear reads >= 16384
-    features runs that layer through ``split_tf32_linear`` (faster, ~6e-5 relative -- see there)."""
+
+class PackedEncoder:
+    """``encoder_x`` + ``norm`` of one member re-laid-out on the device for ladine_encode (FP16 hi | lo halves of the
+    power-of-two-scaled weights: as many bytes as the FP32 originals)."""
+
+    def __init__(self, model):
+        layers = _kernel_encoder_layers(model)
+        if layers is None:
+            raise NotImplementedError("ladine_encode supports the 'linear' encoder arch (Linear-BN-Softplus x2, Linear, "
+                                      "BatchNorm1d norm) with FP32 CUDA parameters")
+        lins, bns = layers
+        dev = lins[0].weight.device
+        self.device_index = _device_index(dev)
+        self.Dx, self.H, self.F = lins[0].in_features, lins[0].out_features, lins[2].out_features
+        keep = []
+
+        def ptr(t):
+            t = t.detach().to(torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        d = _capi.EncoderDesc()
+        d.struct_size = C.sizeof(_capi.EncoderDesc)
+        d.data_dim, d.hidden_dim, d.feature_dim, d.bn_eps = self.Dx, self.H, self.F, float(bns[0].eps)
+        for l in range(3):
+            d.lin_w[l], d.lin_b[l] = ptr(lins[l].weight), ptr(lins[l].bias)
+            d.bn_w[l], d.bn_b[l] = ptr(bns[l].weight), ptr(bns[l].bias)
+            d.bn_mean[l], d.bn_var[l] = ptr(bns[l].running_mean), ptr(bns[l].running_var)
+        lib = _capi.load()
+        self._h = _capi.handle(self.device_index)
+        out = C.c_void_p()
+        with torch.cuda.device(self.device_index):
+            stream = torch.cuda.current_stream().cuda_stream
+            _capi.check(self._h, lib.ladine_pack_encoder(self._h, C.byref(d), C.c_void_p(stream), C.byref(out)))
+            torch.cuda.current_stream().synchronize()
+        del keep
+        self._ptr = out.value
+        self.nbytes = int(lib.ladine_encoder_bytes(self._ptr))
+        self._finalizer = weakref.finalize(self, lib.ladine_free_encoder, self._h, self._ptr)
+
+    @property
+    def ptr(self) -> int:
+        return self._ptr
+
+
+_ENC_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def packed_encoder_of(model) -> Optional[PackedEncoder]:
+    """Pack ``model``'s encoder once (re-packed when an encoder / norm parameter changes); None when the kernel does
+    not cover this encoder (other archs, CPU parameters, train mode)."""
+    if getattr(model, "training", False) or _kernel_encoder_layers(model) is None:
+        return None
+    fp = _encoder_fingerprint(model)
+    hit = _ENC_CACHE.get(model)
+    if hit is not None and hit[0] == fp:
+        return hit[1]
+    pe = PackedEncoder(model)
+    _ENC_CACHE[model] = (fp, pe)
+    return pe
+
+
+def encode_members(models: Sequence, x: torch.Tensor, mode: str = "auto") -> torch.Tensor:
+    """``[K, N, F]`` step-invariant features ``norm(encoder_x_k(x))`` of K members on the same images.
+
+    mode "auto": ONE ladine_encode call (the images are split into FP16 hi + lo operands once for all members) when every
+    member's encoder is covered by the kernel and ``x`` is a CUDA tensor; otherwise member by member through
+    ``encode_features``.  "torch" forces the PyTorch modules, "kernel" raises instead of falling back."""
+    if mode not in ("auto", "kernel", "torch", "fp32", "tf32x3"):
+        raise ValueError("mode must be auto, kernel, torch, fp32 or tf32x3")
+    if mode in ("auto", "kernel") and x.is_cuda and x.dim() == 2 and x.shape[0] > 0:
+        encs = [packed_encoder_of(m) for m in models]
+        ok = all(e is not None for e in encs) and len({(e.Dx, e.H, e.F, e.device_index) for e in encs}) == 1
+        if ok and encs[0].Dx == x.shape[1] and encs[0].device_index == _device_index(x.device):
+            K, N = len(encs), x.shape[0]
+            xin = x.detach().to(torch.float32).contiguous()
+            out = torch.empty((K, N, encs[0].F), dtype=torch.float32, device=x.device)
+            lib = _capi.load()
+            h = _capi.handle(encs[0].device_index)
+            arr = (C.c_void_p * K)(*[e.ptr for e in encs])
+            with torch.cuda.device(encs[0].device_index):
+                stream = torch.cuda.current_stream().cuda_stream
+                _capi.check(h, lib.ladine_encode(h, arr, K, C.c_void_p(xin.data_ptr()), N, C.c_void_p(out.data_ptr()),
+                                                 C.c_void_p(stream)))
+            return out
+        if mode == "kernel":
+            raise NotImplementedError("ladine_encode does not cover these encoders / this input (see PackedEncoder)")
+    tmode = "fp32" if mode in ("auto", "kernel", "torch") else mode
+    return torch.stack([_encode_torch(m, x, tmode) for m in models])
+
+
+def encode_features(model, x: torch.Tensor, mode: str = "auto") -> torch.Tensor:
+    """``norm(encoder_x(x))`` (step-invariant; latent_model.py:170-171) -> [N, F].
+
+    mode "auto" (default): libladine's encoder kernel when it covers this encoder (see ``encode_members``), else the
+    PyTorch modules.  "torch" / "fp32": the module as is.  "tf32x3": PyTorch with the image-sized first Linear through
+    ``split_tf32_linear`` (~6e-5 relative).  "kernel": libladine or an error."""
+    return encode_members([model], x, mode)[0]
+
+
+def _encode_torch(model, x: torch.Tensor, mode: str = "fp32") -> torch.Tensor:
     with torch.no_grad():
         enc = getattr(model, "encoder_x", None)
         first = enc[0] if isinstance(enc, torch.nn.Sequential) and len(enc) > 0 else None
@@ -195,6 +315,8 @@ def encode_features(model, x: torch.Tensor, mode: str = "fp32") -> torch.Tensor:
 
 def encoder_backend(model) -> str:
     """What evaluates ``norm(encoder_x(x))`` for this model (reported by bench.py)."""
+    if not getattr(model, "training", False) and _kernel_encoder_layers(model) is not None:
+        return "libladine enc_gemm_kernel (tcgen05, FP16 hi+lo split operands, FP32-grade)"
     return "PyTorch FP32 GEMMs (cuBLAS)"
 
 

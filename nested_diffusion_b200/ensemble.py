@@ -83,8 +83,9 @@ class NestedEnsemble:
         return len(self.members)
 
     def encode(self, x: torch.Tensor) -> torch.Tensor:
-        """[K, N, F] step-invariant features, one encoder pass per member (PyTorch GEMMs)."""
-        return torch.stack([engine.encode_features(m, x) for m in self.models])
+        """[K, N, F] step-invariant features: one ladine_encode call for all members (PyTorch modules for encoder
+        archs the kernel does not cover)."""
+        return engine.encode_members(self.models, x)
 
     def sample(self, x: torch.Tensor, y0hats, draws: int, n_steps: int, alphas, one_minus_alphas_bar_sqrt, *,
                y_T_means=None, noise: Optional[torch.Tensor] = None, seed: Optional[int] = None,

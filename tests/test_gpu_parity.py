@@ -161,6 +161,54 @@ def _single_gemm_layer(F, rows, prec):
     assert (got_eps - want_eps).abs().max() <= 2e-5 * max(1.0, float(want_eps.abs().max()))
 
 
+@pytest.mark.parametrize("ctas", [1, 2, 3])
+@pytest.mark.parametrize("F,rows", [(512, 300), (4096, 200)])
+def test_split_gemm_layer_is_fp32_grade(F, rows, ctas):
+    """FP32X at the level of ONE layer: tcgen05 GEMM on FP16 hi+lo operands (three K segments, main + correction
+    accumulators, chunked promotion into FP32 registers) + fused epilogue vs torch FP64 on the UNROUNDED FP32 operands.
+    Bar: 1e-6 of the layer's largest output (a K=4096 FP32 dot product carries ~3e-7 of rounding noise).  `ctas` is
+    ignored by this path (always 128 x 128 tiles): the three runs check that the option does not disturb it."""
+    import ctypes as C
+
+    from nested_diffusion_b200 import _capi, engine
+
+    T, Cc = 4, 2
+    sd = orc.synth_state_dict(7, F, 16, 16, Cc, T)
+    pm = engine.PackedMember({k: v.cuda() for k, v in sd.items()}, n_steps=T, precision="fp32x")
+    p = orc.fold_member(sd, T, torch.float64)
+    g = torch.Generator().manual_seed(1)
+    rows_pad = (rows + 255) // 256 * 256
+    h32 = torch.zeros(rows_pad, pm.Fp)
+    h32[:rows, :F] = torch.rand(rows, F, generator=g) * 2
+    hi = h32.half()
+    lo = (h32 - hi.float()).half()
+    h_in = torch.cat([hi, lo], dim=1).contiguous().cuda()            # [rows_pad, 2 Fp]: hi | lo
+    exact_in = (hi.double() + lo.double())[:rows, :F]
+    lib, h = _capi.load(), _capi.handle(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    t = 2
+    engine.set_option(0, "ctas", ctas)
+    try:
+        h_out = torch.zeros(rows_pad, 2 * pm.Fp, dtype=torch.float16, device="cuda")
+        _capi.check(h, lib.ladine_debug_layer(h, pm.ptr, 2, t, h_in.data_ptr(), rows, h_out.data_ptr(), None, stream))
+        NB = pm.Fp // 256
+        part = torch.zeros(rows_pad, NB, 2, pm.Cp, device="cuda")
+        _capi.check(h, lib.ladine_debug_layer(h, pm.ptr, 3, t, h_in.data_ptr(), rows, None, part.data_ptr(), stream))
+        torch.cuda.synchronize()
+    finally:
+        engine.set_option(0, "ctas", 0)
+    want = torch.nn.functional.softplus(p["A2"][t] * (exact_in @ p["W2"].T) + p["C2"][t])
+    ho = h_out.cpu().double()
+    got = (ho[:rows, :F] + ho[:rows, pm.Fp:pm.Fp + F])
+    err2 = float((got - want).abs().max() / want.abs().max())
+    h3 = torch.nn.functional.softplus(p["A3"][t] * (exact_in @ p["W3"].T) + p["C3"][t])
+    want_eps = h3 @ p["W4"].T
+    got_eps = part[:rows, :, :, :Cc].double().sum(dim=(1, 2)).cpu()
+    err3 = float((got_eps - want_eps).abs().max() / max(1.0, float(want_eps.abs().max())))
+    print(f"F={F} ctas={ctas}: layer-2 output rel err {err2:.2e}, lin4 partial sum rel err {err3:.2e}")
+    assert err2 <= 1e-6 and err3 <= 1e-6
+
+
 @pytest.mark.parametrize("name", ["tc_f256_t200", "tc_f512_t100"])
 def test_pair_mode_chain_matches_reference_golden(name, pair_mode):
     test_chain_matches_reference_golden(name)
@@ -543,6 +591,36 @@ def test_runner_shim_matches_restated_reference_loop():
     want_piw = orc.mean_piw_per_class(torch.cat(y_all, dim=1), mv, tgt)
     for got, want in zip((tester.last_metrics["piw_correct"], tester.last_metrics["piw_incorrect"]), want_piw):
         assert torch.allclose(got, want, atol=1e-4, equal_nan=True)
+
+
+@pytest.mark.parametrize("Dx,H,F,N", [(1000, 200, 300, 70), (4096, 256, 128, 1), (640, 128, 4096, 300)])
+def test_encoder_kernel_is_fp32_grade(Dx, H, F, N):
+    """ladine_encode (FP16 hi+lo split operands on tcgen05, chunked FP32 promotion, split-K + fixed-order finish) vs
+    the same encoder in torch FP64, beside PyTorch's own FP32 result: ragged K / N padding, one row, several row tiles."""
+    from nested_diffusion_b200 import engine
+
+    meta = dict(T=4, C=2, Dx=Dx, F=F, H=H, guidance=True)
+    sd = orc.synth_state_dict(31, F, H, Dx, 2, 4)
+    model = make_model(meta, sd)
+    g = torch.Generator().manual_seed(8)
+    x = torch.rand(N, Dx, generator=g).cuda()
+    with torch.no_grad():
+        got = engine.encode_features(model, x, mode="kernel")
+        ref32 = engine.encode_features(model, x, mode="torch")
+        want = orc.encoder_features({k: v.double() for k, v in sd.items() if v.is_floating_point()} |
+                                    {k: v for k, v in sd.items() if not v.is_floating_point()}, x.cpu().double())
+    scale = float(want.abs().max())
+    e_k = float((got.cpu().double() - want).abs().max()) / scale
+    e_t = float((ref32.cpu().double() - want).abs().max()) / scale
+    print(f"encoder Dx={Dx} H={H} F={F} N={N}: kernel {e_k:.2e}, torch fp32 {e_t:.2e} (rel to max |xf| = {scale:.2f})")
+    assert got.shape == (N, F) and torch.isfinite(got).all()
+    assert e_k <= 3e-6
+    # K members in one call == member by member
+    model2 = make_model(meta, orc.synth_state_dict(32, F, H, Dx, 2, 4))
+    with torch.no_grad():
+        both = engine.encode_members([model, model2], x, mode="kernel")
+        assert torch.equal(both[0], got)
+        assert torch.equal(both[1], engine.encode_features(model2, x, mode="kernel"))
 
 
 def test_split_tf32_encoder_option_accuracy():

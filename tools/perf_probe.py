@@ -12,8 +12,7 @@ lanes = int(sys.argv[7]) if len(sys.argv) > 7 else 2
 engine.set_option(0, "lanes", lanes)
 ctas = int(sys.argv[8]) if len(sys.argv) > 8 else 0
 engine.set_option(0, "ctas", ctas)
-pdl = int(sys.argv[9]) if len(sys.argv) > 9 else 1
-engine.set_option(0, "pdl", pdl)
+pdl = 0  # programmatic dependent launch was removed in round 2 (argv[9] kept for positional compatibility)
 fuse = int(sys.argv[10]) if len(sys.argv) > 10 else 0
 engine.set_option(0, "fuse", fuse)
 tail_vec = int(sys.argv[11]) if len(sys.argv) > 11 else 0
