@@ -85,6 +85,17 @@ SYMBOLS = {
 _lib = None
 _lock = threading.Lock()
 _handles = {}
+_call_locks = {}
+
+
+def call_lock(device_index: int) -> "threading.Lock":
+    """Serialises the C-ABI calls that use one handle's workspace (ctypes releases the GIL, so two Python threads could
+    otherwise interleave ladine_sample / ladine_encode on the same handle; the header requires serialisation)."""
+    with _lock:
+        lk = _call_locks.get(device_index)
+        if lk is None:
+            lk = _call_locks[device_index] = threading.Lock()
+    return lk
 
 
 class LadineError(RuntimeError):

@@ -249,6 +249,13 @@ int fill_ids(ladine_handle* h, const ladine_sample_args& a, int k0, int kn, Chai
 }  // namespace
 
 namespace ladine {
+cudaError_t order_after_previous_call(ladine_handle* h, cudaStream_t st) {
+  if (!h->ev_done) return cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
+  return cudaStreamWaitEvent(st, h->ev_done, 0);
+}
+void mark_call_done(ladine_handle* h, cudaStream_t st) {
+  if (h->ev_done) cudaEventRecord(h->ev_done, st);
+}
 cudaError_t launch_guidance_u(const ladine_member* const* members, int K, int N, const float* y0hat, float* u,
                               cudaStream_t st) {
   GuidanceParams p{};
@@ -308,6 +315,7 @@ int ladine_destroy(ladine_handle* h) {
       if (h->ev_join[l]) cudaEventDestroy(h->ev_join[l]);
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
   }
   delete h;
   return LADINE_OK;
@@ -502,6 +510,9 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
 
   const StepCoef* h_coef = reinterpret_cast<const StepCoef*>(a->coef);
   static_assert(sizeof(StepCoef) == 8 * sizeof(float), "coef rows are 8 floats");
+  // the handle's workspace is shared by successive calls: order this call after the previous one even when the
+  // caller switched streams (a no-op when both are on the same stream)
+  if (ladine::order_after_previous_call(h, st) != cudaSuccess) return fail(h, LADINE_ERR_CUDA, "stream ordering event");
 
   // Tensor path: member groups advance concurrently on up to `lanes` streams (lane 0 = caller's stream).
   // The resident path is a single launch per group and needs no lanes.
@@ -620,6 +631,7 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
     if (je == cudaSuccess) je = cudaStreamWaitEvent(st, h->ev_join[l], 0);
     if (je != cudaSuccess && status == LADINE_OK) status = fail_cuda(h, je, "lane join");
   }
+  ladine::mark_call_done(h, st);
   return status;
 }
 

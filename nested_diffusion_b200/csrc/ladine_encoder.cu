@@ -321,6 +321,7 @@ int ladine_encode(ladine_handle* h, const ladine_encoder* const* encoders, int32
   }
   EncDeviceGuard guard(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (order_after_previous_call(h, st) != cudaSuccess) return efail(h, LADINE_ERR_CUDA, "stream ordering event");
   std::string err;
   cudaError_t ce = resolve_encode(h, &err);
   if (ce != cudaSuccess) return efail(h, LADINE_ERR_CUDA, err);
@@ -444,6 +445,7 @@ int ladine_encode(ladine_handle* h, const ladine_encoder* const* encoders, int32
     return efail(h, LADINE_ERR_CUDA, buf);
   }
   h->last_encoder_launches = launches;
+  mark_call_done(h, st);
   return LADINE_OK;
 }
 

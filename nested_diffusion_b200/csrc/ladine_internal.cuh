@@ -65,6 +65,9 @@ struct ladine_handle {
   int tail_vec = 0;          // tail/head features per thread: 0 = pick by wave quantisation, else 4 or 8
   double pair_gain = 1.08;   // measured throughput ratio pair/single per useful tile (see choose_ctas)
   cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};  // [0] unused: caller's stream
+  // end of the last ladine_sample / ladine_encode on this handle: the next call's stream waits for it before it touches
+  // the shared workspace, so calls issued on DIFFERENT streams are ordered instead of overwriting each other
+  cudaEvent_t ev_done = nullptr;
   cudaEvent_t ev_fork = nullptr;
   cudaEvent_t ev_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
   bool profiling = false;
@@ -106,6 +109,10 @@ size_t sched_bytes_bound(int K, int rows, int NB);
 int64_t debug_plan(int K, int rows, int Fp, int geometry, int row_major, int units, int32_t* table_out, int64_t cap,
                    int32_t info_out[4]);
 size_t tensor_gemm_smem_bytes(int Cp);
+
+// ---- cross-stream ordering of the calls that share a handle's workspaces (ladine_api.cu) ----
+cudaError_t order_after_previous_call(ladine_handle* h, cudaStream_t st);
+void mark_call_done(ladine_handle* h, cudaStream_t st);
 
 // ---- shared small kernels (ladine_api.cu) ----
 cudaError_t launch_guidance_u(const ladine_member* const* members, int K, int N, const float* y0hat, float* u,

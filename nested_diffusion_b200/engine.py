@@ -125,7 +125,10 @@ def packed_member_of(model, precision: str = "auto") -> PackedMember:
     hit = _PACK_CACHE.get(model)
     if hit is not None and hit[0] == fp:
         return hit[1]
-    pm = PackedMember(model.state_dict(), precision=precision)
+    eps = {float(getattr(model, f"unetnorm{l}").eps) for l in (1, 2, 3) if hasattr(model, f"unetnorm{l}")}
+    if len(eps) > 1:
+        raise NotImplementedError("unetnorm1..3 with different eps values are not supported by the folded tables")
+    pm = PackedMember(model.state_dict(), precision=precision, bn_eps=eps.pop() if eps else 1e-5)
     _PACK_CACHE[model] = (fp, pm)
     return pm
 
@@ -278,7 +281,7 @@ def encode_members(models: Sequence, x: torch.Tensor, mode: str = "auto") -> tor
             lib = _capi.load()
             h = _capi.handle(encs[0].device_index)
             arr = (C.c_void_p * K)(*[e.ptr for e in encs])
-            with torch.cuda.device(encs[0].device_index):
+            with torch.cuda.device(encs[0].device_index), _capi.call_lock(encs[0].device_index):
                 stream = torch.cuda.current_stream().cuda_stream
                 _capi.check(h, lib.ladine_encode(h, arr, K, C.c_void_p(xin.data_ptr()), N, C.c_void_p(out.data_ptr()),
                                                  C.c_void_p(stream)))
@@ -440,7 +443,7 @@ def sample_chains(members: Sequence[PackedMember], xf: torch.Tensor, y0hat: torc
     lib = _capi.load()
     h = _capi.handle(m0.device_index)
     arr = (C.c_void_p * K)(*[m.ptr for m in members])
-    with torch.cuda.device(m0.device_index):
+    with torch.cuda.device(m0.device_index), _capi.call_lock(m0.device_index):
         a.stream = torch.cuda.current_stream().cuda_stream
         _capi.check(h, lib.ladine_sample(h, arr, C.byref(a)))
     out = {"y": y_out}

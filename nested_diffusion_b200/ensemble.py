@@ -74,6 +74,7 @@ class NestedEnsemble:
         if len(models) < 1:
             raise ValueError("need at least one member")
         self.models = list(models)
+        self.precision = precision
         self.members: List[engine.PackedMember] = [engine.packed_member_of(m, precision) for m in models]
         self.member_ids = list(member_ids) if member_ids is not None else list(range(len(models)))
         self.device = self.members[0].device
@@ -92,6 +93,14 @@ class NestedEnsemble:
                temperature: Optional[float] = None, xf: Optional[torch.Tensor] = None, image_offset: int = 0,
                images_total: int = 0, draw_offset: int = 0, draws_total: int = 0) -> EnsembleResult:
         """All K x ``draws`` chains for the images in ``x`` ([N, ...]); ``y0hats``: [K, N, C] or list of K [N, C]."""
+        # members fine-tuned / reloaded in place since the last call are re-packed (a cheap fingerprint hit otherwise);
+        # train-mode BatchNorm (batch statistics) is not what the folded tables compute
+        for m in self.models:
+            if getattr(m, "training", False):
+                raise NotImplementedError("NestedEnsemble.sample needs members in eval() mode (train-mode BatchNorm uses "
+                                          "batch statistics; the kernels fold the running statistics)")
+        if self.models:
+            self.members = [engine.packed_member_of(m, self.precision) for m in self.models]
         y0hats = torch.stack(list(y0hats)) if not torch.is_tensor(y0hats) else y0hats
         mus = y0hats if y_T_means is None else (
             torch.stack(list(y_T_means)) if not torch.is_tensor(y_T_means) else y_T_means)

