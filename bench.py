@@ -269,10 +269,21 @@ def run_gpu_arm(args):
     out_host = torch.empty(2, N_IMAGES, K_MEMBERS * DRAWS, N_CLASSES).pin_memory()
     lo, hi = nd.shard_bounds(N_IMAGES, rank, world)
 
-    def hot_path(x, yh, seed, draws=DRAWS, temperature=TEMPERATURE, ensemble=ens):
+    state = {"weights": None, "events": []}
+
+    def hot_path(x, yh, seed, draws=DRAWS, temperature=TEMPERATURE, ensemble=ens, balanced=True):
         """the public call a user makes: encoder features + all chains + probabilities + the gather"""
         with torch.no_grad():
-            return nd.sample_ensemble(ensemble, x, yh, draws, T_STEPS, alphas, omabs, seed=seed, temperature=temperature)
+            return nd.sample_ensemble(ensemble, x, yh, draws, T_STEPS, alphas, omabs, seed=seed, temperature=temperature,
+                                      shard_weights=state["weights"] if balanced else None,
+                                      local_events=state["events"])
+
+    def local_ms():
+        """this rank's own sampling time (without the wait at the gather) per call since the last reset"""
+        torch.cuda.synchronize()
+        ms = [a.elapsed_time(b) for a, b in state["events"]]
+        state["events"] = []
+        return sum(ms) / max(1, len(ms))
 
     def timed(fn, steps, collective=True):
         if world > 1 and collective:
@@ -303,12 +314,39 @@ def run_gpu_arm(args):
 
     for i in range(args.warmup):
         step_resident(-1 - i)
+    balance = None
+    if world > 1:
+        # The GPUs of one box do not run at the same speed under the 1 kW cap (measured spread of the per-rank sampling
+        # time at N=8: 719-758 ms), and a sharded step ends with the slowest rank: record each rank's own time.  With
+        # --balance the image tiles are sized by that speed (the samples do not depend on the partition: global Philox
+        # ids); it is off by default because image-granular tiles fall off the 256-row tile grid (see --balance).
+        mine = torch.tensor([local_ms()], device=device)
+        allms = torch.empty(world, device=device)
+        dist.all_gather_into_tensor(allms, mine)
+        equal = [nd.shard_bounds(N_IMAGES, r, world) for r in range(world)]
+        speed = [(b - a) / max(1e-3, float(t)) for (a, b), t in zip(equal, allms.tolist())]
+        if not args.no_balance:
+            state["weights"] = speed
+        step_resident(-100)
+        balance = {"equal_tiles_local_ms": [round(float(t), 1) for t in allms.tolist()],
+                   "weights": [round(v / max(speed), 4) for v in speed], "enabled": not args.no_balance,
+                   "images_per_rank": [b - a for a, b in (nd.weighted_bounds(N_IMAGES, speed) if not args.no_balance else equal)]}
+        local_ms()
+    state["events"] = []
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ms_total = timed(step_resident, args.steps)          # the headline region: no per-kernel events inside
     clocks = sampler.stop() if rank == 0 else None
     launches_per_step = engine.last_launches(local_rank)
+    if world > 1:
+        mine = torch.tensor([local_ms()], device=device)
+        allms = torch.empty(world, device=device)
+        dist.all_gather_into_tensor(allms, mine)
+        balance["timed_local_ms"] = [round(float(t), 1) for t in allms.tolist()]
+        lo, hi = (nd.weighted_bounds(N_IMAGES, state["weights"]) if state["weights"] else
+                  [nd.shard_bounds(N_IMAGES, r, world) for r in range(world)])[rank]
+    state["events"] = []
     # second pass (at most 2 steps) with every GEMM / tail-head launch bracketed by CUDA events on the launching
     # stream (ladine_set_profiling): per-kernel durations for the roofline, kept out of the headline region
     prof_steps = min(args.steps, 2)
@@ -332,7 +370,7 @@ def run_gpu_arm(args):
     yh2 = torch.softmax(2 * torch.randn(K_MEMBERS, N_IMAGES_C2, N_CLASSES, generator=g2), -1).to(device)
 
     def step_c2(i):
-        hot_path(x2, yh2, 900 + i, temperature=TEMPERATURE_C2)
+        hot_path(x2, yh2, 900 + i, temperature=TEMPERATURE_C2, balanced=False)
 
     for i in range(2):
         step_c2(-1 - i)
@@ -437,6 +475,8 @@ def run_gpu_arm(args):
             "roofline": roof,
         }
         line.update(extras)
+        if balance is not None:
+            line["load_balance"] = balance
         if world == 1:
             cpu = CpuReference()
             n_explicit = 20
@@ -460,6 +500,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32x"])
+    ap.add_argument("--balance", dest="no_balance", action="store_false", default=True,
+                    help="N>1: size the image tiles by measured rank speed (sample_ensemble(shard_weights=...)) instead of "
+                         "equally.  Off by default: measured on 8 B200s it LOSES 4 % (129.9 k vs 135.0 k samples/s) because "
+                         "128 images x 20 draws = exactly 10 pair tiles per member, and one more image costs a whole tile round")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

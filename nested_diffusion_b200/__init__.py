@@ -8,7 +8,8 @@ ensemble.sample_ensemble) and the ensemble statistics (stats).
 """
 from . import diffusion_utils, latent_model, schedule, stats  # noqa: F401
 from .engine import PackedMember, fill_noise, packed_member_of, sample_chains  # noqa: F401
-from .ensemble import NestedEnsemble, gather_image_shards, sample_ensemble, shard_bounds  # noqa: F401
+from .ensemble import (NestedEnsemble, gather_image_shards, sample_ensemble, shard_bounds,  # noqa: F401
+                       weighted_bounds)
 from .latent_model import ConditionalLinear, ConditionalModel  # noqa: F401
 
 __version__ = "0.1.0"

@@ -30,10 +30,28 @@ def padded_shard_size(n_items: int, world: int) -> int:
     return -(-n_items // world)
 
 
-def gather_image_shards(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor:
+def weighted_bounds(n_items: int, weights: Sequence[float]) -> List[Tuple[int, int]]:
+    """Contiguous partition of ``range(n_items)`` into ``len(weights)`` shards whose sizes follow ``weights`` (the
+    measured relative speed of each rank: the GPUs of one box differ by several per cent under the 1 kW power cap, and a
+    step of the sharded sampler ends when the SLOWEST rank is done).  Every rank must pass the same weights.  Because
+    the Philox streams are keyed on global (member, draw, image) ids, the partition does not change a single sample."""
+    w = [max(float(x), 0.0) for x in weights]
+    if not w or sum(w) <= 0:
+        raise ValueError("weights must contain a positive entry")
+    total, acc, edges = sum(w), 0.0, [0]
+    for x in w[:-1]:
+        acc += x
+        edges.append(min(n_items, max(edges[-1], int(round(n_items * acc / total)))))
+    edges.append(n_items)
+    return [(edges[i], edges[i + 1]) for i in range(len(w))]
+
+
+def gather_image_shards(local: torch.Tensor, n_items: int, group=None,
+                        bounds: Optional[Sequence[Tuple[int, int]]] = None) -> torch.Tensor:
     """All-gather per-rank tensors ``[n_local, ...]`` (image-major) into ``[n_items, ...]`` on every rank.
 
-    Equal-count collective: shards are zero-padded to ``ceil(n_items / world)`` rows, gathered with one
+    Equal-count collective: shards are zero-padded to the largest shard (``ceil(n_items / world)`` rows for the default
+    balanced partition; ``bounds`` gives the per-rank ``(lo, hi)`` of a weighted one), gathered with one
     ``all_gather_into_tensor`` (NCCL over NVLink on the B200 box, gloo in the CPU tests) and trimmed."""
     import torch.distributed as dist
 
@@ -43,18 +61,19 @@ def gather_image_shards(local: torch.Tensor, n_items: int, group=None) -> torch.
         return local
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    lo, hi = shard_bounds(n_items, rank, world)
+    if bounds is None:
+        bounds = [shard_bounds(n_items, r, world) for r in range(world)]
+    if len(bounds) != world:
+        raise ValueError("need one (lo, hi) per rank")
+    lo, hi = bounds[rank]
     if local.shape[0] != hi - lo:
         raise ValueError(f"rank {rank} should hold {hi - lo} images, got {local.shape[0]}")
-    per = padded_shard_size(n_items, world)
+    per = max(1, max(b - a for a, b in bounds))
     send = local.new_zeros((per,) + tuple(local.shape[1:]))
     send[: hi - lo] = local
     recv = local.new_empty((world * per,) + tuple(local.shape[1:]))
     dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
-    parts = []
-    for r in range(world):
-        rlo, rhi = shard_bounds(n_items, r, world)
-        parts.append(recv[r * per: r * per + (rhi - rlo)])
+    parts = [recv[r * per: r * per + (bounds[r][1] - bounds[r][0])] for r in range(world)]
     return torch.cat(parts, dim=0)
 
 
@@ -131,7 +150,8 @@ class NestedEnsemble:
 
 def sample_ensemble(models_or_ensemble, x, y0hats, draws, n_steps, alphas, one_minus_alphas_bar_sqrt, *,
                     seed: Optional[int] = None, temperature: Optional[float] = None, group=None,
-                    precision: str = "auto"):
+                    precision: str = "auto", shard_weights: Optional[Sequence[float]] = None,
+                    local_events: Optional[list] = None):
     """Sharded nested-ensemble sampling + the single all-gather.
 
     Every rank passes the SAME full ``x`` [N, ...] and ``y0hats`` [K, N, C]; each samples its image
@@ -139,7 +159,10 @@ def sample_ensemble(models_or_ensemble, x, y0hats, draws, n_steps, alphas, one_m
     (member, draw, image) ids -- so the gathered result is identical for any world size -- and
     returns on every rank ``(y0 [N, K*D, C], probs [N, K*D, C] or None)`` in image-major order.
     ``x`` / ``y0hats`` may live on the HOST (pinned memory makes the copy asynchronous): only this rank's
-    image tile is copied to the device."""
+    image tile is copied to the device.  ``shard_weights`` (one entry per rank, identical on all ranks) sizes the
+    image tiles by measured rank speed instead of equally (``weighted_bounds``); the result is the same either way.
+    ``local_events``: a list that receives one ``(start, end)`` pair of CUDA events around this rank's own sampling
+    (before the gather), for load-balance measurements."""
     import torch.distributed as dist
 
     ens = models_or_ensemble if isinstance(models_or_ensemble, NestedEnsemble) else NestedEnsemble(
@@ -155,8 +178,17 @@ def sample_ensemble(models_or_ensemble, x, y0hats, draws, n_steps, alphas, one_m
             box = [seed]
             dist.broadcast_object_list(box, src=0, group=group)
             seed = box[0]
-    lo, hi = shard_bounds(N, rank, world)
+    if shard_weights is not None and world > 1:
+        if len(shard_weights) != world:
+            raise ValueError("shard_weights needs one entry per rank")
+        bounds = weighted_bounds(N, shard_weights)
+    else:
+        bounds = [shard_bounds(N, r, world) for r in range(world)]
+    lo, hi = bounds[rank]
     K, D = ens.K, int(draws)
+    if local_events is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     C = y0hats.shape[-1]
     if hi > lo:
         x_local, yh_local = x[lo:hi], y0hats[:, lo:hi]
@@ -171,7 +203,10 @@ def sample_ensemble(models_or_ensemble, x, y0hats, draws, n_steps, alphas, one_m
     else:
         y_local = torch.empty((0, K * D, C), dtype=torch.float32, device=ens.device)
         p_local = torch.empty_like(y_local) if temperature is not None else None
+    if local_events is not None:
+        ev[1].record()
+        local_events.append(ev)
     if p_local is not None:
-        both = gather_image_shards(torch.cat([y_local, p_local], dim=-1).contiguous(), N, group)
+        both = gather_image_shards(torch.cat([y_local, p_local], dim=-1).contiguous(), N, group, bounds)
         return both[..., :C].contiguous(), both[..., C:].contiguous()
-    return gather_image_shards(y_local.contiguous(), N, group), None
+    return gather_image_shards(y_local.contiguous(), N, group, bounds), None

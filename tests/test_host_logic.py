@@ -359,6 +359,20 @@ def test_shard_bounds_partition():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_weighted_bounds_partition():
+    """Speed-weighted image tiles: contiguous, exhaustive, proportional; degenerate weights give empty tiles, not errors."""
+    for n in (1, 7, 70, 1024):
+        for w in ([1.0], [1.0, 1.0], [1.0, 0.9, 1.1], [0.96, 1.0, 1.0, 1.02, 0.99, 1.0, 0.95, 1.0], [1.0, 0.0, 1.0]):
+            spans = nd.weighted_bounds(n, w)
+            assert len(spans) == len(w) and spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] and spans[i][0] <= spans[i][1] for i in range(len(w) - 1))
+            for (a, b), wi in zip(spans, w):
+                assert abs((b - a) - n * wi / sum(w)) <= 1.0
+    assert nd.weighted_bounds(1024, [1.0] * 8) == [nd.shard_bounds(1024, r, 8) for r in range(8)]
+    with pytest.raises(ValueError):
+        nd.weighted_bounds(10, [0.0, 0.0])
+
+
 _WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
@@ -372,6 +386,11 @@ full = torch.randn(n, 100, 2, generator=g)           # [N, K*D, C] "samples" eve
 lo, hi = nd.shard_bounds(n, rank, world)
 got = nd.gather_image_shards(full[lo:hi].contiguous(), n)
 assert torch.equal(got, full), "gathered tensor differs from the unsharded one"
+# speed-weighted (uneven) image tiles gather to the same tensor
+bounds = nd.weighted_bounds(n, [1.0, 0.55])
+wlo, whi = bounds[rank]
+got_w = nd.gather_image_shards(full[wlo:whi].contiguous(), n, bounds=bounds)
+assert torch.equal(got_w, full), "weighted shards gather differently"
 mv = stats.majority_voting_for_mc_samples(got.permute(1, 0, 2))
 ref = stats.majority_voting_for_mc_samples(full.permute(1, 0, 2))
 assert torch.equal(mv, ref)
