@@ -384,21 +384,30 @@ def run_gpu_arm(args):
         "steps": c2_steps}
 
     if world == 1:
-        # ---- config 1: one member, 64 images, one draw (the module-swap call shape) ----
-        ens1 = nd.NestedEnsemble(models[:1], precision=args.precision)
-        x1, yh1 = x_dev[:N_IMAGES_C1], yh_dev[:1, :N_IMAGES_C1]
+        # ---- config 1: one member, 64 images, one draw = the reference's own call, through the drop-in p_sample_loop ----
+        from nested_diffusion_b200 import diffusion_utils as du
 
-        def step_c1(i):
-            hot_path(x1, yh1, 700 + i, draws=1, ensemble=ens1)
+        x1, yh1 = x_dev[:N_IMAGES_C1], yh_dev[0, :N_IMAGES_C1].contiguous()
 
-        for i in range(2):
-            step_c1(-1 - i)
+        def step_c1(i, persistent=True):
+            with torch.no_grad():   # a fresh image tensor every call: the encoder prologue runs inside the region
+                du.p_sample_loop(models[0], x1.clone(), yh1, yh1, T_STEPS, alphas, omabs, only_last_sample=True,
+                                 seed=700 + i, persistent=persistent)
+
         c1_steps = 10
-        ms_c1 = timed(step_c1, c1_steps)
-        extras["config1"] = {"workload": f"one member, N={N_IMAGES_C1} images, 1 draw = {N_IMAGES_C1} chains",
-                             "value": N_IMAGES_C1 * c1_steps / (ms_c1 / 1e3), "unit": "samples/s",
-                             "ms_per_step": ms_c1 / c1_steps, "us_per_reverse_step": 1e3 * ms_c1 / c1_steps / T_STEPS,
-                             "steps": c1_steps}
+        res_c1 = {}
+        for tag, pers in (("persistent", True), ("tile_kernels", False)):
+            for i in range(2):
+                step_c1(-1 - i, pers)
+            ms_c1 = timed(lambda i: step_c1(i, pers), c1_steps, collective=False)
+            res_c1[tag] = {"value": N_IMAGES_C1 * c1_steps / (ms_c1 / 1e3), "ms_per_step": ms_c1 / c1_steps,
+                           "us_per_reverse_step": 1e3 * ms_c1 / c1_steps / T_STEPS,
+                           "gpu_launches_per_call": engine.last_launches(local_rank)}
+        extras["config1"] = {"workload": f"one member, N={N_IMAGES_C1} images, 1 draw = {N_IMAGES_C1} chains, drop-in "
+                                         "diffusion_utils.p_sample_loop (encoder prologue included)",
+                             "unit": "samples/s", "steps": c1_steps, **res_c1["persistent"],
+                             "kernel": "persistent_chain_kernel: ONE cooperative launch per chain (split-K over the SMs)",
+                             "three_launches_per_step": res_c1["tile_kernels"]}
         # ---- encoder and sampler timed separately (north_star: the input provider is "timed separately") ----
         with torch.no_grad():
             xf = ens.encode(x_dev)

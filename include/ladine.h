@@ -159,6 +159,10 @@ uint64_t ladine_workspace_bytes(const ladine_handle* h);
  *       when the rows pad well and slim tiles when the call is so small that twice as many tiles still fit the
  *       SMs in one round; all geometries give bit-identical results;
  *   "pair_gain_permille": measured per-tile speed ratio pair/single used by the auto choice (default 1080);
+ *   "persist" (0 default | 1): calls of <= 4 members x <= 128 chains run as ONE cooperative launch for the whole chain
+ *       (split-K over all SMs, grid barriers between the phases of a step, chain state in shared memory) instead of
+ *       three launches per reverse step: ~3x faster for the reference's own call shape (one member, 70 images, one
+ *       draw); split-K sums differ from the tile kernels' by FP32 rounding noise, hence opt-in;
  *   "fuse" (0 default | 1): run the tail + head of each reverse step inside the layer-3 GEMM kernel (helper warps
  *       gated by per-row-group arrival counters) instead of a separate kernel; bitwise identical results;
  *   "order" (0 auto | 1 | 2): GEMM tile order -- N-tile-major (a W tile stays hot while a member's rows stream past

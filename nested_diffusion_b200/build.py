@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", f) for f in ("ladine_api.cu", "ladine_resident.cu", "ladine_tensor.cu", "ladine_split.cu", "ladine_encoder.cu")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("ladine_api.cu", "ladine_resident.cu", "ladine_tensor.cu", "ladine_split.cu", "ladine_encoder.cu", "ladine_persist.cu")]
 HDR = [os.path.join(HERE, "csrc", f) for f in ("ladine_common.cuh", "ladine_internal.cuh", "ladine_tc.cuh", "ladine_tensor.cuh", "ladine_split.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "ladine.h")]
 OUT = os.path.join(HERE, "lib", "libladine.so")

@@ -514,6 +514,33 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
   // caller switched streams (a no-op when both are on the same stream)
   if (ladine::order_after_previous_call(h, st) != cudaSuccess) return fail(h, LADINE_ERR_CUDA, "stream ordering event");
 
+  // Small calls, opt-in: the whole chain in ONE cooperative launch (split-K over all SMs, grid barriers between phases)
+  const int pS = (tensor && !m0->split && h->persist) ? persist_splits(h, a->K, a->N * a->D, Fp, C) : 0;
+  if (pS > 0) {
+    uint64_t off = 0;
+    const uint64_t o_coef = off; off = align_up(off + (uint64_t)a->T * sizeof(StepCoef), 1024);
+    const uint64_t o_u = off; off = align_up(off + (uint64_t)a->K * a->N * Fp * 4, 1024);
+    const uint64_t o_ws = off; off += persist_workspace_bytes(a->K, Fp, Cp, pS);
+    rc = ensure_workspace(h, off);
+    if (rc != LADINE_OK) return rc;
+    uint8_t* ws = static_cast<uint8_t*>(h->ws);
+    cudaError_t e = cudaMemcpyAsync(ws + o_coef, a->coef, (size_t)a->T * sizeof(StepCoef), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail_cuda(h, e, "coefficient upload");
+    ChainIds ids{};
+    rc = fill_ids(h, *a, 0, a->K, &ids);
+    if (rc != LADINE_OK) return rc;
+    float* d_u = reinterpret_cast<float*>(ws + o_u);
+    e = launch_guidance_u(members, a->K, a->N, a->y0hat, d_u, st);
+    if (e != cudaSuccess) return fail_cuda(h, e, "guidance projection kernel");
+    h->last_launches += 1;
+    std::string err;
+    e = launch_persistent_chain(h, members, *a, ids, reinterpret_cast<const StepCoef*>(ws + o_coef), d_u, ws + o_ws, pS,
+                                si.n_slots, si.n_traj, st, &h->last_launches, &err);
+    ladine::mark_call_done(h, st);
+    if (e != cudaSuccess) return err.empty() ? fail_cuda(h, e, "persistent chain launch") : fail(h, LADINE_ERR_CUDA, err);
+    return LADINE_OK;
+  }
+
   // Tensor path: member groups advance concurrently on up to `lanes` streams (lane 0 = caller's stream).
   // The resident path is a single launch per group and needs no lanes.
   int lanes = tensor ? h->lanes : 1;
@@ -644,6 +671,14 @@ int ladine_set_option(ladine_handle* h, const char* key, int64_t value) {
   }
   if (strcmp(key, "fuse") == 0) {
     h->fuse = value != 0;
+    return LADINE_OK;
+  }
+  if (strcmp(key, "persist") == 0) {
+    h->persist = value != 0;
+    return LADINE_OK;
+  }
+  if (strcmp(key, "persist_debug") == 0) {
+    h->persist_debug = value != 0;
     return LADINE_OK;
   }
   if (strcmp(key, "ctas") == 0) {

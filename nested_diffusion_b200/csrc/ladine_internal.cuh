@@ -60,6 +60,10 @@ struct ladine_handle {
   // Bitwise identical to the separate tail/head kernel; measured 1-3 % SLOWER at config 2 (the helpers compete with
   // the SMEM-port-bound mainloop and the last row groups drain after the last MMA), so it is opt-in.
   bool fuse = false;
+  // small calls (<= 4 members x <= 128 chains) on the whole-chain persistent kernel (ladine_persist.cu): opt-in because its
+  // split-K sums differ from the tile kernels' by FP32 rounding noise (the tile path is bitwise partition-invariant)
+  bool persist = false;
+  bool persist_debug = false;   // block 0 of the persistent kernel prints its per-phase clock totals
   int ctas = 0;             // 0 = choose per call, 1 = cta_group::1, 2 = cta_group::2 CTA pairs
   int order = 0;             // GEMM tile order: 0 = auto, 1 = N-tile-major, 2 = row-major
   int tail_vec = 0;          // tail/head features per thread: 0 = pick by wave quantisation, else 4 or 8
@@ -109,6 +113,13 @@ size_t sched_bytes_bound(int K, int rows, int NB);
 int64_t debug_plan(int K, int rows, int Fp, int geometry, int row_major, int units, int32_t* table_out, int64_t cap,
                    int32_t info_out[4]);
 size_t tensor_gemm_smem_bytes(int Cp);
+
+// ---- whole-chain persistent kernel for small calls (ladine_persist.cu) ----
+int persist_splits(const ladine_handle* h, int K, int rows, int Fp, int C);   // K slices per layer, 0 = not applicable
+size_t persist_workspace_bytes(int K, int Fp, int Cp, int S);
+cudaError_t launch_persistent_chain(ladine_handle* h, const ladine_member* const* members, const ladine_sample_args& a,
+                                    const ChainIds& ids, const StepCoef* d_coef, const float* d_u, uint8_t* ws, int S,
+                                    int n_slots, int n_traj, cudaStream_t st, int64_t* launches, std::string* err);
 
 // ---- cross-stream ordering of the calls that share a handle's workspaces (ladine_api.cu) ----
 cudaError_t order_after_previous_call(ladine_handle* h, cudaStream_t st);

@@ -72,7 +72,7 @@ def _prepare(model, x, y_0_hat, y_T_mean, output_detach, precision):
 
 def p_sample_loop(model, x, y_0_hat, y_T_mean, n_steps, alphas, one_minus_alphas_bar_sqrt, only_last_sample=False,
                   input_model_original_version=True, output_detach=True, *, noise=None, seed=None, precision="auto",
-                  draws=None):
+                  draws=None, persistent=True):
     """Full reverse chain y_T -> y_0, diffusion_utils.py:133-163.
 
     Returns y_0 ``[B, C]`` when ``only_last_sample`` else the list ``[y_T, ..., y_1, y_0]`` of
@@ -80,7 +80,11 @@ def p_sample_loop(model, x, y_0_hat, y_T_mean, n_steps, alphas, one_minus_alphas
 
     ``draws=D`` (keyword-only extension) runs D independent chains per input row in ONE launch -- what the runner
     obtains with D sequential calls (classification_train_separately.py:770-777) -- and returns ``[D, B, C]``
-    (needs ``only_last_sample=True``; ``noise``, if given, is ``[D, n_steps, B, C]``)."""
+    (needs ``only_last_sample=True``; ``noise``, if given, is ``[D, n_steps, B, C]``).
+
+    ``persistent`` (default True): a call of at most 128 chains at a tensor-core width runs as ONE cooperative launch
+    for the whole chain (``engine.sample_chains(persistent=True)``) -- the shape of the runner's own calls (70 images,
+    one draw); larger calls use the tile kernels either way."""
     if not input_model_original_version:
         model = model.conditional_model
     pm, xf, yh, mu = _prepare(model, x, y_0_hat, y_T_mean, output_detach, precision)
@@ -96,7 +100,7 @@ def p_sample_loop(model, x, y_0_hat, y_T_mean, n_steps, alphas, one_minus_alphas
             noise = noise.reshape(1, D, n_steps, B, Cc)
         elif seed is None:
             seed = engine.fresh_seed()
-        return engine.sample_chains([pm], xf, yh, mu, coef, D, noise=noise, seed=seed or 0)["y"][0]
+        return engine.sample_chains([pm], xf, yh, mu, coef, D, noise=noise, seed=seed or 0, persistent=persistent)["y"][0]
     if noise is not None:
         if noise.shape[0] < n_steps or tuple(noise.shape[1:]) != (B, Cc):
             raise ValueError(f"noise must be [n_steps={n_steps}, {B}, {Cc}]")
@@ -104,14 +108,14 @@ def p_sample_loop(model, x, y_0_hat, y_T_mean, n_steps, alphas, one_minus_alphas
     elif seed is None:
         seed = engine.fresh_seed()
     out = engine.sample_chains([pm], xf, yh, mu, coef, 1, noise=noise, seed=seed or 0,
-                               trajectory=not only_last_sample)
+                               trajectory=not only_last_sample, persistent=persistent)
     if only_last_sample:
         return out["y"][0, 0]
     return list(out["traj"][0, 0].unbind(0))
 
 
 def p_sample(model, x, y, y_0_hat, y_T_mean, t, alphas, one_minus_alphas_bar_sqrt, output_detach=True, *,
-             noise=None, seed=None, precision="auto"):
+             noise=None, seed=None, precision="auto", persistent=True):
     """One reverse step y_t -> y_{t-1} at table index ``t`` (>= 1), diffusion_utils.py:54-92."""
     t = int(t)
     if t < 1:
@@ -123,12 +127,12 @@ def p_sample(model, x, y, y_0_hat, y_T_mean, t, alphas, one_minus_alphas_bar_sqr
     elif seed is None:
         seed = engine.fresh_seed()
     out = engine.sample_chains([pm], xf, yh, mu, coef, 1, t_first=t, t_last=t, y_init=y.reshape(1, 1, *y.shape),
-                               noise=noise, seed=seed or 0)
+                               noise=noise, seed=seed or 0, persistent=persistent)
     return out["y"][0, 0]
 
 
 def p_sample_t_1to0(model, x, y, y_0_hat, y_T_mean, one_minus_alphas_bar_sqrt, output_detach=True, *,
-                    precision="auto"):
+                    precision="auto", persistent=True):
     """Last reverse step y_1 -> y_0 (table index 0, no noise), diffusion_utils.py:96-111."""
     pm, xf, yh, mu = _prepare(model, x, y_0_hat, y_T_mean, output_detach, precision)
     # row 0 of the coefficient table needs only one_minus_alphas_bar_sqrt[0]
@@ -136,5 +140,6 @@ def p_sample_t_1to0(model, x, y, y_0_hat, y_T_mean, one_minus_alphas_bar_sqrt, o
     q = (1 - s.square()).sqrt()
     coef = torch.zeros(1, 8)
     coef[0, 0], coef[0, 1], coef[0, 2] = (1 / q)[0], (1 - q)[0], s[0]
-    out = engine.sample_chains([pm], xf, yh, mu, coef, 1, t_first=0, t_last=0, y_init=y.reshape(1, 1, *y.shape))
+    out = engine.sample_chains([pm], xf, yh, mu, coef, 1, t_first=0, t_last=0, y_init=y.reshape(1, 1, *y.shape),
+                               persistent=persistent)
     return out["y"][0, 0]

@@ -372,12 +372,17 @@ def sample_chains(members: Sequence[PackedMember], xf: torch.Tensor, y0hat: torc
                   y_init: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None, seed: int = 0,
                   member_ids: Optional[Sequence[int]] = None, image_offset: int = 0, images_total: int = 0,
                   draw_offset: int = 0, draws_total: int = 0, trajectory: bool = False,
-                  temperature: Optional[float] = None):
+                  temperature: Optional[float] = None, persistent: bool = False):
     """One ``ladine_sample`` call: K members x ``draws`` x N images, steps t_first .. t_last.
 
     xf [K,N,F], y0hat/ytmean [K,N,C] (CUDA, FP32); coef: HOST [T,8] from ``schedule.coef_table``.
     Returns ``y`` [K,D,N,C] (plus ``traj`` [K,D,n_traj,N,C] and/or ``probs`` [K,D,N,C] when asked),
     enqueued on the current CUDA stream without host synchronisation.
+
+    ``persistent=True`` lets a SMALL call (<= 4 members x <= 128 chains each, 16-bit tensor path) run as one cooperative
+    launch for the whole chain (ladine_persist.cu: split-K over all SMs, chain state on chip) instead of three launches
+    per reverse step -- ~3x faster at the reference's own call shape; its split-K sums differ from the tile kernels' by
+    FP32 rounding noise, so the default (False) keeps results bitwise independent of how a batch is partitioned.
     """
     K = len(members)
     if K < 1:
@@ -445,6 +450,7 @@ def sample_chains(members: Sequence[PackedMember], xf: torch.Tensor, y0hat: torc
     arr = (C.c_void_p * K)(*[m.ptr for m in members])
     with torch.cuda.device(m0.device_index), _capi.call_lock(m0.device_index):
         a.stream = torch.cuda.current_stream().cuda_stream
+        _capi.check(h, lib.ladine_set_option(h, b"persist", int(bool(persistent))))
         _capi.check(h, lib.ladine_sample(h, arr, C.byref(a)))
     out = {"y": y_out}
     if traj is not None:

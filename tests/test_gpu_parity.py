@@ -715,6 +715,60 @@ def test_shape_matrix_vs_oracle(F, C, guidance, K, N, D, T, prec):
     assert torch.allclose(got["probs"].cpu(), orc.convert_to_prob(got["y"].cpu(), 0.3), atol=2e-6)
 
 
+@pytest.mark.parametrize("F,K,N,D,C,T,prec", [
+    (4096, 1, 70, 1, 2, 40, "fp16"),      # the runner's own call shape: one member, 70 images, one draw; S = 8 slices
+    (4096, 1, 64, 2, 2, 12, "bf16"),      # 128 rows: a full row tile
+    (512, 2, 33, 3, 3, 9, "fp16"),        # two members (32 CTAs), 99 rows, C = 3 -> Cp = 4, S = 8 of 8 K blocks
+    (256, 4, 1, 1, 2, 5, "fp16"),         # a single chain per member, four members, S = 4
+    (1024, 3, 10, 4, 10, 6, "fp16"),      # ten classes (Cp = 16)
+])
+def test_persistent_chain_kernel_matches_tile_path_and_oracle(F, K, N, D, C, T, prec):
+    """The whole-chain cooperative kernel (one launch, split-K over the SMs, 5 grid barriers per step) vs the
+    three-launches-per-step tile path on the same Philox noise (FP32 rounding noise apart: split-K sums), vs the oracle's
+    packed form with the same operand rounding, run-to-run bitwise determinism, trajectory / probabilities / y_init."""
+    import nested_diffusion_b200 as nd
+    from nested_diffusion_b200 import engine
+    from nested_diffusion_b200.schedule import coef_table
+
+    dev = torch.device("cuda")
+    sds = [_rand_trunk_sd(3000 + k, F, C, T, dev) for k in range(K)]
+    pms = [nd.PackedMember(sd, n_steps=T, precision=prec) for sd in sds]
+    g = torch.Generator(device="cuda").manual_seed(4)
+    xf = torch.randn(K, N, F, device=dev, generator=g)
+    yh = torch.softmax(torch.randn(K, N, C, device=dev, generator=g), -1)
+    alphas, omabs = orc.schedule_tensors(orc.make_beta_schedule("linear", max(T, 2), 1e-4, 0.02))
+    alphas, omabs = alphas[:T], omabs[:T]
+    coef = coef_table(alphas, omabs, T)
+    kw = dict(seed=91, trajectory=True, temperature=0.25)
+    tile = engine.sample_chains(pms, xf, yh, yh, coef, D, **kw)
+    n_tile = engine.last_launches(0)
+    pers = engine.sample_chains(pms, xf, yh, yh, coef, D, persistent=True, **kw)
+    n_pers = engine.last_launches(0)
+    assert n_pers == 2 and n_tile == 2 + 3 * T, (n_pers, n_tile)      # guidance projection + ONE chain kernel
+    again = engine.sample_chains(pms, xf, yh, yh, coef, D, persistent=True, **kw)
+    for name in ("y", "traj", "probs"):
+        assert torch.equal(pers[name], again[name]), f"{name}: run-to-run determinism"
+        assert torch.isfinite(pers[name]).all()
+    tol = 2e-4 if prec == "bf16" else 2e-5
+    assert rel_err(pers["traj"].cpu(), tile["traj"].cpu()) <= tol
+    assert torch.allclose(pers["probs"].cpu(), orc.convert_to_prob(pers["y"].cpu(), 0.25), atol=2e-6)
+    assert torch.equal(pers["traj"][:, :, -1], pers["y"])
+    # the oracle's packed form on the replayed noise (one member is enough at the wide shapes)
+    noise = engine.fill_noise("cuda", K, N, D, C, T, 91).cpu()
+    for k in range(K if F <= 1024 else 1):
+        sd_cpu = {kk: v.cpu() for kk, v in sds[k].items()}
+        with torch.no_grad():
+            want = torch.stack([orc.packed_sample(sd_cpu, xf[k].cpu(), yh[k].cpu(), yh[k].cpu(), T, alphas, omabs,
+                                                  noise[k, d], operand_dtype=ODT[prec]) for d in range(D)])
+        assert rel_err(pers["y"][k].cpu(), want) <= (2e-4 if prec == "bf16" else 2e-5)
+    # continuing a chain from a caller-supplied state (p_sample's call shape)
+    if T >= 5:
+        y_in = tile["traj"][:, :, 2].contiguous()      # y after two steps
+        a = engine.sample_chains(pms, xf, yh, yh, coef, D, t_first=T - 3, t_last=T - 4, y_init=y_in, seed=5, persistent=True)
+        b = engine.sample_chains(pms, xf, yh, yh, coef, D, t_first=T - 3, t_last=T - 4, y_init=y_in, seed=5)
+        assert rel_err(a["y"].cpu(), b["y"].cpu()) <= tol
+
+
 def _rand_trunk_sd(seed, F, Cc, T, dev):
     """A random trunk state-dict generated ON the GPU (the full-width members would take minutes on the host)."""
     gg = torch.Generator(device="cuda").manual_seed(seed)
