@@ -16,7 +16,7 @@ from nested_diffusion_b200.schedule import make_beta_schedule, schedule_tensors 
 draws = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 dev = torch.device("cuda", 0)
 models = bench.build_members(dev)
-K, N, T = len(models), bench.N_IMAGES, bench.T_STEPS
+K, N, T = len(models), bench.N_IMAGES_C2, bench.T_STEPS   # the ChestXRay test batch: 70 images
 alphas, omabs = schedule_tensors(make_beta_schedule("linear", T, 1e-4, 0.02))
 alphas, omabs = alphas.to(dev), omabs.to(dev)
 g = torch.Generator().manual_seed(1)
@@ -33,7 +33,7 @@ def level1():
 
 def level2(ens):
     with torch.no_grad():
-        return ens.sample(x, yh, draws, T, alphas, omabs, temperature=bench.TEMPERATURE).y0
+        return ens.sample(x, yh, draws, T, alphas, omabs, temperature=bench.TEMPERATURE_C2).y0
 
 for name, fn in (("level 1: K x draws sequential p_sample_loop calls", level1),
                  ("level 2: one NestedEnsemble.sample call", None)):
