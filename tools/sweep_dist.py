@@ -60,7 +60,7 @@ def cpu_reference(T, N, D):
     return v * bench.T_STEPS / T, cpu.kind, cpu.cores, steps
 
 
-def run(T, D, N, budget_rowsteps=7e8):
+def run(T, D, N, budget_rowsteps=float(os.environ.get("SWEEP_BUDGET", "7e8")), reps=int(os.environ.get("SWEEP_REPS", "3"))):
     members = [nd.PackedMember(_rand_trunk_sd(s, F, C, min(T, 1000), dev), n_steps=min(T, 1000), precision="fp16")
                for s in range(K)]
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -72,7 +72,7 @@ def run(T, D, N, budget_rowsteps=7e8):
     steps = int(max(8, min(T, budget_rowsteps * world // rows)))
     alphas, omabs = schedule_tensors(make_beta_schedule("linear", steps, 1e-4, 0.02))
     best = None
-    for it in range(3):
+    for it in range(reps):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
