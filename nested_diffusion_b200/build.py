@@ -11,7 +11,7 @@ SRC = [os.path.join(HERE, "csrc", f) for f in ("ladine_api.cu", "ladine_resident
 HDR = [os.path.join(HERE, "csrc", f) for f in ("ladine_common.cuh", "ladine_internal.cuh", "ladine_tc.cuh", "ladine_tensor.cuh", "ladine_split.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "ladine.h")]
 OUT = os.path.join(HERE, "lib", "libladine.so")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-cudart", "shared", "-Xcompiler", "-fPIC"]
 
 
 def nvcc_path() -> str:
@@ -78,7 +78,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed compiling " + obj)
         if verbose:
             sys.stderr.write(log)
-    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] +
+    # the CUDA runtime is linked DYNAMICALLY (libcudart.so.12: torch's copy when torch is loaded first, else the
+    # toolkit's): a statically linked runtime would carry every runtime entry point's name -- the batch-copy calls the
+    # B200 pool forbids among them -- in the shipped binary although the library never calls them
+    r = subprocess.run([nvcc, "-shared", "-cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] +
                        [o for o, _, _ in results], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
