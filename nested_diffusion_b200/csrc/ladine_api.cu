@@ -536,9 +536,16 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
     std::string err;
     e = launch_persistent_chain(h, members, *a, ids, reinterpret_cast<const StepCoef*>(ws + o_coef), d_u, ws + o_ws, pS,
                                 si.n_slots, si.n_traj, st, &h->last_launches, &err);
-    ladine::mark_call_done(h, st);
-    if (e != cudaSuccess) return err.empty() ? fail_cuda(h, e, "persistent chain launch") : fail(h, LADINE_ERR_CUDA, err);
-    return LADINE_OK;
+    if (e == cudaSuccess) {
+      ladine::mark_call_done(h, st);
+      return LADINE_OK;
+    }
+    if (e != cudaErrorCooperativeLaunchTooLarge)
+      return err.empty() ? fail_cuda(h, e, "persistent chain launch") : fail(h, LADINE_ERR_CUDA, err);
+    // not every CTA of the cooperative grid can be resident right now (the occupancy check runs before anything of the
+    // chain is enqueued): use the tile kernels for this call
+    cudaGetLastError();
+    h->last_launches = 0;
   }
 
   // Tensor path: member groups advance concurrently on up to `lanes` streams (lane 0 = caller's stream).

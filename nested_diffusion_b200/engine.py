@@ -106,30 +106,72 @@ class PackedMember:
 
 
 # ------------------------------------------------------------------------------------------------
-# module -> PackedMember cache (re-packed when any trunk parameter is modified in place or moved)
+# module -> PackedMember cache.  A pack is reused while the parameters it was made from are unchanged:
+#   * in-place edits (optimizer steps, load_state_dict, copy_) bump the tensors' version counters -> re-pack;
+#   * a device move replaces the storages but not the values -- the reference's runner shuttles every member CPU -> GPU -> CPU
+#     per batch (classification_train_separately.py:773, :780) -- so when only the storage addresses changed, a strided content
+#     checksum decides: equal -> the pack (which lives on the GPU) is kept, different -> re-pack.
 # ------------------------------------------------------------------------------------------------
 _PACK_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+_CHECKSUM_SAMPLES = 4096
 
 
-def _trunk_fingerprint(model) -> tuple:
+def _select(model, trunk: bool):
     sd = model.state_dict(keep_vars=True)
-    return tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in sd.items()
-                 if k.startswith(("lin", "unetnorm")) and v.is_floating_point())
+    return [(k, v) for k, v in sd.items() if v.is_floating_point() and k.startswith(("lin", "unetnorm")) == trunk]
+
+
+def _versions(tensors) -> tuple:
+    return tuple((k, v._version, tuple(v.shape)) for k, v in tensors)
+
+
+def _addresses(tensors) -> tuple:
+    return tuple((v.data_ptr(), str(v.device)) for _, v in tensors)
+
+
+def _checksum(tensors) -> tuple:
+    """Strided sample sums of every tensor (one small device->host copy): detects a storage swap with new values."""
+    parts = []
+    for _, v in tensors:
+        flat = v.detach().reshape(-1)
+        step = max(1, flat.numel() // _CHECKSUM_SAMPLES)
+        smp = flat[::step].double()
+        parts.append(torch.stack([smp.sum(), (smp * smp).sum()]).cpu())
+    return tuple(float(x) for x in torch.cat(parts).tolist()) if parts else ()
+
+
+class _Cached:
+    __slots__ = ("versions", "addresses", "checksum", "extra", "value")
+
+    def __init__(self, tensors, extra, value):
+        self.versions, self.addresses, self.extra, self.value = _versions(tensors), _addresses(tensors), extra, value
+        self.checksum = _checksum(tensors)
+
+    def valid_for(self, tensors, extra) -> bool:
+        if self.extra != extra or self.versions != _versions(tensors):
+            return False
+        addr = _addresses(tensors)
+        if addr == self.addresses:
+            return True
+        if _checksum(tensors) != self.checksum:    # storages were replaced (e.g. .to(device)): same values?
+            return False
+        self.addresses = addr
+        return True
 
 
 def packed_member_of(model, precision: str = "auto") -> PackedMember:
-    """Pack ``model`` (a ConditionalModel-shaped nn.Module) once and reuse it across calls."""
+    """Pack ``model`` (a ConditionalModel-shaped nn.Module) once and reuse it across calls (see the cache rules above)."""
     if isinstance(model, PackedMember):
         return model
-    fp = (_trunk_fingerprint(model), precision)
+    tensors = _select(model, True)
     hit = _PACK_CACHE.get(model)
-    if hit is not None and hit[0] == fp:
-        return hit[1]
+    if hit is not None and hit.valid_for(tensors, precision):
+        return hit.value
     eps = {float(getattr(model, f"unetnorm{l}").eps) for l in (1, 2, 3) if hasattr(model, f"unetnorm{l}")}
     if len(eps) > 1:
         raise NotImplementedError("unetnorm1..3 with different eps values are not supported by the folded tables")
     pm = PackedMember(model.state_dict(), precision=precision, bn_eps=eps.pop() if eps else 1e-5)
-    _PACK_CACHE[model] = (fp, pm)
+    _PACK_CACHE[model] = _Cached(tensors, precision, pm)
     return pm
 
 
@@ -254,12 +296,12 @@ def packed_encoder_of(model) -> Optional[PackedEncoder]:
     not cover this encoder (other archs, CPU parameters, train mode)."""
     if getattr(model, "training", False) or _kernel_encoder_layers(model) is None:
         return None
-    fp = _encoder_fingerprint(model)
+    tensors = _select(model, False)
     hit = _ENC_CACHE.get(model)
-    if hit is not None and hit[0] == fp:
-        return hit[1]
+    if hit is not None and hit.valid_for(tensors, None):
+        return hit.value
     pe = PackedEncoder(model)
-    _ENC_CACHE[model] = (fp, pe)
+    _ENC_CACHE[model] = _Cached(tensors, None, pe)
     return pe
 
 
@@ -326,12 +368,6 @@ def encoder_backend(model) -> str:
 _XF_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 
-def _encoder_fingerprint(model) -> tuple:
-    sd = model.state_dict(keep_vars=True)
-    return tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in sd.items()
-                 if not k.startswith(("lin", "unetnorm")))
-
-
 def features_of(model, x: torch.Tensor) -> torch.Tensor:
     """``encode_features(model, x)``, remembered for the LAST ``x`` of each model.
 
@@ -339,13 +375,15 @@ def features_of(model, x: torch.Tensor) -> torch.Tensor:
     (classification_train_separately.py:770-777) and re-evaluates the 2.4 GB encoder layer inside every one of the
     T steps of every call; the drop-in evaluates it once per call, and with this cache once per (member, batch).
     A hit needs the same tensor OBJECT (a strong reference is kept, so its address cannot be recycled), an unchanged
-    in-place version counter, and unchanged encoder / norm parameters; the returned features are read-only."""
-    key = (_encoder_fingerprint(model), x._version, tuple(x.shape), x.dtype, bool(getattr(model, "training", False)))
+    in-place version counter, and unchanged encoder / norm parameters (same rules as the pack caches: version
+    counters, and a content checksum when only the storages moved); the returned features are read-only."""
+    tensors = _select(model, False)
+    extra = (x._version, tuple(x.shape), x.dtype, str(x.device), bool(getattr(model, "training", False)))
     hit = _XF_CACHE.get(model)
-    if hit is not None and hit[0] is x and hit[1] == key:
-        return hit[2]
+    if hit is not None and hit[0] is x and hit[1].valid_for(tensors, extra):
+        return hit[1].value
     xf = encode_features(model, x)
-    _XF_CACHE[model] = (x, key, xf)
+    _XF_CACHE[model] = (x, _Cached(tensors, extra, xf))
     return xf
 
 

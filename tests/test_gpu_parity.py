@@ -488,6 +488,44 @@ def test_encoder_features_are_remembered_per_image_tensor_only():
     assert engine.features_of(model, xc) is not f2
 
 
+def test_pack_caches_survive_the_runners_device_shuttle():
+    """The reference's runner moves every member CPU -> GPU -> CPU per batch (classification_train_separately.py:773,
+    :780).  That replaces the parameters' storages but not their values: the packed member / packed encoder / cached
+    features must be kept (version counters unchanged + content checksum equal), while an in-place edit or a storage
+    swap with NEW values must re-pack."""
+    from nested_diffusion_b200 import diffusion_utils as du
+    from nested_diffusion_b200 import engine
+
+    fx = ChainFixture("tc_f256_t200")
+    m = fx.meta
+    sd, x, yhat, noise, alphas, omabs = fx.materialize()
+    model = make_model(m, sd)
+    xc, yc, nc = x.cuda(), yhat.cuda(), noise.cuda()
+
+    def run():
+        with torch.no_grad():
+            return du.p_sample_loop(model, xc, yc, yc, m["T"], alphas, omabs, only_last_sample=True, noise=nc)
+
+    first = run()
+    pm, pe, xf = engine.packed_member_of(model), engine.packed_encoder_of(model), engine.features_of(model, xc)
+    model.to("cpu")
+    model.to("cuda")                                   # new storages, same values
+    assert engine.packed_member_of(model) is pm and engine.packed_encoder_of(model) is pe
+    assert engine.features_of(model, xc) is xf
+    assert torch.equal(run(), first)
+    with torch.no_grad():
+        model.lin2.lin.weight.mul_(1.01)               # in-place edit: version counter moves
+    pm2 = engine.packed_member_of(model)
+    assert pm2 is not pm and engine.packed_encoder_of(model) is pe
+    second = run()
+    assert not torch.equal(second, first)
+    model.lin4.bias.data = model.lin4.bias.data + 0.5  # storage swap WITH new values, no version bump: checksum catches it
+    assert engine.packed_member_of(model) is not pm2
+    model.norm.bias.data = model.norm.bias.data + 0.25
+    assert engine.packed_encoder_of(model) is not pe and engine.features_of(model, xc) is not xf
+    assert not torch.equal(run(), second)
+
+
 def test_empty_and_single_row_batches():
     """Edge shapes of the drop-in: an empty batch is a valid call (the reference's ops are no-ops on [0, C]) and a
     single row must equal the same row sampled inside a larger batch on the same injected noise."""
