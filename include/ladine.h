@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LADINE_ABI_VERSION 1
+#define LADINE_ABI_VERSION 2   /* 2: LADINE_PREC_FP32X, ladine_pack_encoder / ladine_encode, option "persist" */
 #define LADINE_MAX_CLASSES 16   /* num_classes supported by the fused kernels            */
 #define LADINE_MAX_GROUP   8    /* members fused into one launch group (larger K loops)  */
 
@@ -162,7 +162,9 @@ uint64_t ladine_workspace_bytes(const ladine_handle* h);
  *   "persist" (0 default | 1): calls of <= 4 members x <= 128 chains run as ONE cooperative launch for the whole chain
  *       (split-K over all SMs, grid barriers between the phases of a step, chain state in shared memory) instead of
  *       three launches per reverse step: ~3x faster for the reference's own call shape (one member, 70 images, one
- *       draw); split-K sums differ from the tile kernels' by FP32 rounding noise, hence opt-in;
+ *       draw); split-K sums differ from the tile kernels' by FP32 rounding noise, hence opt-in; when the cooperative grid
+ *       cannot be fully resident the call falls back to the tile kernels.  "persist_debug" (0 | 1): block 0 of that
+ *       kernel prints its per-phase clock totals (device printf) at the end of the chain;
  *   "fuse" (0 default | 1): run the tail + head of each reverse step inside the layer-3 GEMM kernel (helper warps
  *       gated by per-row-group arrival counters) instead of a separate kernel; bitwise identical results;
  *   "order" (0 auto | 1 | 2): GEMM tile order -- N-tile-major (a W tile stays hot while a member's rows stream past

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libladine.so lacks {name} declared in include/ladine.h"
     assert sorted(_capi.SYMBOLS) == declared, "ctypes binding and header disagree"
-    assert lib.ladine_version() == 1
+    assert lib.ladine_version() == 2
 
 
 def test_struct_sizes_match_header_layout():

@@ -42,11 +42,19 @@ xf = torch.randn(K, N, F, device=dev, generator=g)
 yh = torch.softmax(torch.randn(K, N, C, device=dev, generator=g), -1)
 alphas, omabs = schedule_tensors(make_beta_schedule("linear", T, 1e-4, 0.02))
 coef = coef_table(alphas, omabs, T)
+import os  # noqa: E402
+for kv in os.environ.get("LADINE_OPTIONS", "").split(","):   # e.g. LADINE_OPTIONS=tail_vec=4,order=2
+    if "=" in kv:
+        engine.set_option(0, kv.split("=")[0], int(kv.split("=")[1]))
+engine.set_profiling(0, True)
 for i in range(2):
     torch.cuda.synchronize()
+    engine.get_profile(0)
     t0 = time.perf_counter()
     out = engine.sample_chains(pms, xf, yh, yh, coef, D, seed=3, t_first=T - 1, t_last=T - n_steps)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    prof = engine.get_profile(0)
     print(f"{prec}: {n_steps} reverse steps of {K * N * D} chains: {1e6 * dt / n_steps:.1f} us/step, "
-          f"launches {engine.last_launches(0)}, finite {bool(torch.isfinite(out['y']).all())}")
+          f"launches {engine.last_launches(0)}, finite {bool(torch.isfinite(out['y']).all())}; per launch (us): "
+          + ", ".join(f"{k} {1e3 * v[0] / max(1, v[1]):.1f}" for k, v in prof.items() if isinstance(v, tuple)))
