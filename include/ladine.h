@@ -170,8 +170,8 @@ uint64_t ladine_workspace_bytes(const ladine_handle* h);
  *   "order" (0 auto | 1 | 2): GEMM tile order -- N-tile-major (a W tile stays hot while a member's rows stream past
  *       it) or row-major (the activations are read once; chosen automatically when a member's activations
  *       exceed 32 MiB and would otherwise be re-read from HBM for every N tile); results are identical;
- *   "tail_vec" (0 auto | 4 | 8): features per thread of the tail/head kernel; auto picks the width whose CTA
- *       count quantises best into waves of resident CTAs (results are identical either way). */
+ *   "tail_vec" (0 default | 4 | 8): features per thread of the tail/head kernel; 4 (the default: more resident warps) was
+ *       faster in every measurement, 8 is kept for A/B timing (results are identical either way). */
 int ladine_set_option(ladine_handle* h, const char* key, int64_t value);
 
 /* Optional per-kernel timing of the tensor-core path.  When enabled, ladine_sample brackets every

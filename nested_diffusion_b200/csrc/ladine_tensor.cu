@@ -520,10 +520,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
 constexpr int kTailThreads = 128;
 constexpr int kTailMaxRows = 32;  // draws handled per CTA
 
-// VEC = features per thread (8 or 4): the host picks the one whose CTA count quantises best into waves of resident
-// CTAs (config 2 with VEC = 8: 1400 CTAs on 148 x 7 slots = 1.35 waves, i.e. a second wave that is one third full).
+// VEC = features per thread: 4 by default (40 registers -> 12 CTAs = 48 warps per SM; measured 376-410 us per launch at
+// config 3 against 456-476 us for VEC = 8 at 64 registers / 8 CTAs), 8 only when forced with the "tail_vec" option.
 template <int MODE, typename T16, int CP, int VEC>
-__global__ void __launch_bounds__(kTailThreads, (CP <= 4 ? 8 : 1)) tailhead_kernel(const __grid_constant__ TailHeadParams p) {
+__global__ void __launch_bounds__(kTailThreads, (CP <= 4 ? (VEC == 4 ? 12 : 8) : 1)) tailhead_kernel(const __grid_constant__ TailHeadParams p) {
   constexpr int kTailCols = kTailThreads * VEC;   // features per CTA
   __shared__ float sY[kTailMaxRows * CP];
   // grid.x = N * colsplit: CTA (n, cs) produces features [cs * kTailCols, (cs+1) * kTailCols) of image n's draws.
@@ -823,26 +823,6 @@ cudaError_t launch_tail(const TailHeadParams& p, dim3 grid, bool bf16, int Cp, i
   return cudaErrorInvalidValue;
 }
 
-// resident CTAs per SM of the mid-step tail/head kernel (what the wave model in TensorChain::init needs)
-template <int VEC>
-int tail_occupancy(bool bf16, int Cp) {
-  int occ = 0;
-#define LADINE_OCC_CASE(CPV)                                                                                         \
-  case CPV:                                                                                                          \
-    if (bf16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tailhead_kernel<kMid, __nv_bfloat16, CPV, VEC>,    \
-                                                            kTailThreads, 0);                                        \
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tailhead_kernel<kMid, __half, CPV, VEC>, kTailThreads, 0); \
-    break;
-  switch (Cp) {
-    LADINE_OCC_CASE(2)
-    LADINE_OCC_CASE(4)
-    LADINE_OCC_CASE(8)
-    LADINE_OCC_CASE(16)
-  }
-#undef LADINE_OCC_CASE
-  return occ > 0 ? occ : 1;
-}
-
 struct ProfSpan {
   ladine_handle* h;
   cudaStream_t st;
@@ -1109,22 +1089,12 @@ struct TensorChain {
     tp.n_traj = n_traj;
     tp.dchunk = a.D < kTailMaxRows ? a.D : kTailMaxRows;
     {
-      // features per thread: the SMs are throughput-bound, so a launch costs ~ ceil(waves) x (resident CTAs x work per
-      // CTA); pick the width whose CTA count quantises best (16 = the per-CTA tail, in element-rows per thread)
-      const long long dchunks = (a.D + tp.dchunk - 1) / tp.dchunk;
-      double best = 0;
-      for (int vec : {8, 4}) {
-        if (h->tail_vec != 0 && h->tail_vec != vec) continue;   // "tail_vec" option: force a width (A/B timing)
-        const int occ = vec == 8 ? tail_occupancy<8>(bf16, Cp) : tail_occupancy<4>(bf16, Cp);
-        const int cs = (Fp + kTailThreads * vec - 1) / (kTailThreads * vec);
-        const long long ctas = (long long)a.N * cs * K * dchunks, slots = (long long)occ * h->sm_count;
-        const double cost = (double)((ctas + slots - 1) / slots) * occ * (vec * tp.dchunk + 16);
-        if (best == 0 || cost < best * 0.97) {   // 8 features per thread unless 4 is clearly better
-          best = cost;
-          tail_vec = vec;
-          tp.colsplit = cs;
-        }
-      }
+      // features per thread: 4 unless forced ("tail_vec").  Measured: 412-417 us against 472-476 us per launch with 8 at
+      // config 3 (102 400 rows; fewer registers -> more resident warps for an issue/latency-bound loop), 42.4 vs 43.9 us
+      // at config 2, 8.5 vs 10.5 us at config 1 -- 8 never won, so the round-1 wave-quantisation model that chose it for
+      // large grids is gone.
+      tail_vec = h->tail_vec == 8 ? 8 : 4;
+      tp.colsplit = (Fp + kTailThreads * tail_vec - 1) / (kTailThreads * tail_vec);
     }
     tgrid = dim3(a.N * tp.colsplit, K, (a.D + tp.dchunk - 1) / tp.dchunk);
     slot_base = a.y_init ? 0 : 1;
