@@ -338,7 +338,7 @@ def run_gpu_arm(args):
         sampler.start()
     ms_total = timed(step_resident, args.steps)          # the headline region: no per-kernel events inside
     clocks = sampler.stop() if rank == 0 else None
-    launches_per_step = engine.last_launches(local_rank)
+    launches_per_step = engine.last_launches(local_rank) + engine.last_encoder_launches(local_rank)
     if world > 1:
         mine = torch.tensor([local_ms()], device=device)
         allms = torch.empty(world, device=device)
@@ -416,6 +416,15 @@ def run_gpu_arm(args):
                                                 temperature=TEMPERATURE, xf=xf), 2, collective=False) / 2
         extras["encoder_ms"] = ms_enc
         extras["sampler_ms"] = ms_smp
+        # the encoder at the ChestXRay batch size (70 images: one row tile, the first layer's 2.35 GB of weights per member
+        # are streamed once, split-K over the SMs): its HBM roofline
+        with torch.no_grad():
+            ens.encode(x2)
+            ms_enc2 = timed(lambda i: ens.encode(x2), 5, collective=False) / 5
+        enc_bytes = K_MEMBERS * 2.0 * (DX * H_DIM + H_DIM * H_DIM + H_DIM * F_DIM) * 2     # FP16 hi + lo of every weight
+        extras["encoder_config2"] = {"ms": ms_enc2, "images": N_IMAGES_C2, "weight_bytes": enc_bytes,
+                                     "achieved_gbs": enc_bytes / (ms_enc2 * 1e-3) / 1e9,
+                                     "note": "weights (FP16 hi|lo = FP32-sized) streamed once per call; HBM-bound regime"}
         extras["encoder_note"] = ("norm(encoder_x(x)) for K members on the whole batch: " + engine.encoder_backend(models[0])
                                   + "; sampler_ms = all chains with xf given")
 

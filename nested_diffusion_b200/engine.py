@@ -499,7 +499,13 @@ def sample_chains(members: Sequence[PackedMember], xf: torch.Tensor, y0hat: torc
 
 
 def last_launches(device_index: int) -> int:
+    """Kernels launched by the last ladine_sample call on this device."""
     return int(_capi.load().ladine_last_launches(_capi.handle(device_index)))
+
+
+def last_encoder_launches(device_index: int) -> int:
+    """Kernels launched by the last ladine_encode call on this device."""
+    return int(_capi.load().ladine_last_encoder_launches(_capi.handle(device_index)))
 
 
 def fill_noise(device, K, N, D, C_cls, T, seed, *, t_first=None, t_last=0, has_init=False, member_ids=None,
