@@ -17,7 +17,7 @@
  *   - work is enqueued on the caller's CUDA stream (cudaStream_t passed as void*); pointers are
  *     borrowed until that stream-ordered work completes.  ladine_sample / ladine_fill_noise never synchronise
  *     with the host in steady state; the exceptions are stated where they occur: the first call that needs a
- *     LARGER workspace than any earlier one (the old buffer is released after a device synchronisation),
+ *     LARGER workspace than any earlier one (the old buffer is released after waiting for the handle's previous call),
  *     ladine_free_member / ladine_destroy (device synchronisation before the buffers are freed) and
  *     ladine_get_profile (waits for the recorded events);
  *   - a handle is bound to one device and is not re-entrant (the caller serialises calls per

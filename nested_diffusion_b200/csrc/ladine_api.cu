@@ -204,7 +204,10 @@ struct DeviceGuard {
 int ensure_workspace(ladine_handle* h, uint64_t bytes) {
   if (bytes <= h->ws_bytes) return LADINE_OK;
   if (h->ws) {
-    cudaDeviceSynchronize();  // earlier stream-ordered work may still read the old buffer
+    // earlier stream-ordered work may still read the old buffer: wait for the handle's last call (calls on one handle
+    // are chained through ev_done, so the latest event covers all of them) -- not for the whole device
+    if (h->ev_done) cudaEventSynchronize(h->ev_done);
+    else cudaDeviceSynchronize();
     cudaFree(h->ws);
     h->ws = nullptr;
     h->ws_bytes = 0;
@@ -810,6 +813,8 @@ int ladine_debug_layer(ladine_handle* h, const ladine_member* member, int layer,
     if (!err.empty()) return fail(h, LADINE_ERR_CUDA, err);
     return fail_cuda(h, e, "debug layer launch");
   }
+  if (!h->ev_done) cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
+  ladine::mark_call_done(h, static_cast<cudaStream_t>(stream));
   return LADINE_OK;
 }
 

@@ -345,7 +345,9 @@ int ladine_encode(ladine_handle* h, const ladine_encoder* const* encoders, int32
   const uint64_t o_sc = off; off = up(off + 64 * sizeof(float), 1024);
   if (off > h->enc_ws_bytes) {
     if (h->enc_ws) {
-      cudaDeviceSynchronize();   // earlier stream-ordered work may still read the old buffer
+      // earlier stream-ordered work may still read the old buffer: wait for the handle's last call
+      if (h->ev_done) cudaEventSynchronize(h->ev_done);
+      else cudaDeviceSynchronize();
       cudaFree(h->enc_ws);
       h->enc_ws = nullptr;
       h->enc_ws_bytes = 0;
