@@ -184,7 +184,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    n_explicit = 10
+    n_explicit = 50       # ~3 s of host work per bench step at 16 cores (the reference re-runs its encoder every step)
     cpu = CpuReference()
     vals, secs = [], []
     for i in range(args.warmup + args.steps):
@@ -383,6 +383,20 @@ def run_gpu_arm(args):
         "value": c2_chains * c2_steps / (ms_c2 / 1e3), "unit": "samples/s", "ms_per_step": ms_c2 / c2_steps,
         "steps": c2_steps}
 
+    if world == 1 and args.precision == "fp16":
+        # ---- the strict mode at config 2: FP32-grade split-operand tensor-core path (north_star's FP32 tolerance:
+        # max-abs <= 1e-4 on y_0 of a trained member, which the 16-bit operand paths do not meet at F=4096) ----
+        ens_x = nd.NestedEnsemble(models, precision="fp32x")
+        step_x = lambda i: hot_path(x2, yh2, 950 + i, temperature=TEMPERATURE_C2, ensemble=ens_x, balanced=False)
+        step_x(-1)
+        ms_x = timed(step_x, 2, collective=False)
+        extras["config2_fp32x"] = {
+            "workload": extras["config2"]["workload"] + ", precision fp32x (FP16 hi+lo split operands, 3 tcgen05.mma per K "
+                        "slice, chunked FP32 promotion): the mode that meets the FP32 tolerance on trained members",
+            "value": c2_chains * 2 / (ms_x / 1e3), "unit": "samples/s", "ms_per_step": ms_x / 2, "steps": 2,
+            "cost_vs_fp16": (ms_x / 2) / (ms_c2 / c2_steps)}
+        del ens_x
+
     if world == 1:
         # ---- config 1: one member, 64 images, one draw = the reference's own call, through the drop-in p_sample_loop ----
         from nested_diffusion_b200 import diffusion_utils as du
@@ -412,8 +426,10 @@ def run_gpu_arm(args):
         with torch.no_grad():
             xf = ens.encode(x_dev)
             ms_enc = timed(lambda i: ens.encode(x_dev), 3, collective=False) / 3
-            ms_smp = timed(lambda i: ens.sample(None, yh_dev, DRAWS, T_STEPS, alphas, omabs, seed=50 + i,
-                                                temperature=TEMPERATURE, xf=xf), 2, collective=False) / 2
+            smp = lambda i: ens.sample(None, yh_dev, DRAWS, T_STEPS, alphas, omabs, seed=50 + i,
+                                       temperature=TEMPERATURE, xf=xf)
+            smp(-1)   # the calls before this one were small (config 1 / 2): bring clocks and caches back to this shape
+            ms_smp = timed(smp, 2, collective=False) / 2
         extras["encoder_ms"] = ms_enc
         extras["sampler_ms"] = ms_smp
         # the encoder at the ChestXRay batch size (70 images: one row tile, the first layer's 2.35 GB of weights per member
@@ -497,7 +513,7 @@ def run_gpu_arm(args):
             line["load_balance"] = balance
         if world == 1:
             cpu = CpuReference()
-            n_explicit = 20
+            n_explicit = 200      # ~12 s of host work at 16 cores
             cpu_v, _ = cpu.run(n_explicit)
             cpu_h, _ = cpu.run(n_explicit, hoisted=True)
             line["cpu_baseline"] = {

@@ -18,8 +18,9 @@
  *     borrowed until that stream-ordered work completes.  ladine_sample / ladine_fill_noise never synchronise
  *     with the host in steady state; the exceptions are stated where they occur: the first call that needs a
  *     LARGER workspace than any earlier one (the old buffer is released after waiting for the handle's previous call),
- *     ladine_free_member / ladine_destroy (device synchronisation before the buffers are freed) and
- *     ladine_get_profile (waits for the recorded events);
+ *     ladine_free_member / ladine_destroy (device synchronisation before the buffers are freed),
+ *     ladine_get_profile (waits for the recorded events) and the packed-image export / import calls (they
+ *     synchronise `stream` so that the HOST buffer is the caller's again on return);
  *   - a handle is bound to one device and is not re-entrant (the caller serialises calls per
  *     handle); distinct handles are independent.
  */
@@ -32,7 +33,8 @@
 extern "C" {
 #endif
 
-#define LADINE_ABI_VERSION 2   /* 2: LADINE_PREC_FP32X, ladine_pack_encoder / ladine_encode, option "persist" */
+#define LADINE_ABI_VERSION 3   /* 2: LADINE_PREC_FP32X, ladine_pack_encoder / ladine_encode, option "persist";
+                                  3: packed images (ladine_*_export / ladine_*_import) */
 #define LADINE_MAX_CLASSES 16   /* num_classes supported by the fused kernels            */
 #define LADINE_MAX_GROUP   8    /* members fused into one launch group (larger K loops)  */
 
@@ -228,6 +230,29 @@ uint64_t ladine_encoder_bytes(const ladine_encoder* enc);
 int ladine_encode(ladine_handle* h, const ladine_encoder* const* encoders, int32_t K, const float* x, int32_t N,
                   float* xf_out, void* stream);
 int64_t ladine_last_encoder_launches(const ladine_handle* h);
+
+/*
+ * Packed images: a packed member / encoder serialised into HOST memory and restored from it, so that a runner can keep
+ * the packed form of a checkpoint on disk (keyed by a hash of the checkpoint's content) and skip building the module,
+ * loading state['noise_estimator'] into it (classification_train_separately.py:684-697) and re-packing on every run.
+ * An image = 128-byte header (magic, ABI version, packed-layout version, dimensions, payload size, checksum) + the packed
+ * device buffers.  Import refuses an image of another ABI / layout version, of the wrong kind, truncated or corrupt
+ * (LADINE_ERR_INVALID, reason in ladine_last_error) -- the caller then packs from the checkpoint again.
+ * host_dst / host_src: HOST pointers (8-byte aligned; pinned memory makes the copies fast).  Both calls synchronise
+ * `stream` before returning, so the host buffer is the caller's again on return.  The image is device-independent:
+ * it may be imported on any handle.
+ */
+uint64_t ladine_member_image_bytes(const ladine_member* m);
+int ladine_member_export(ladine_handle* h, const ladine_member* m, void* host_dst, uint64_t capacity, void* stream);
+int ladine_member_import(ladine_handle* h, const void* host_src, uint64_t bytes, void* stream, ladine_member** out);
+uint64_t ladine_encoder_image_bytes(const ladine_encoder* enc);
+int ladine_encoder_export(ladine_handle* h, const ladine_encoder* enc, void* host_dst, uint64_t capacity, void* stream);
+int ladine_encoder_import(ladine_handle* h, const void* host_src, uint64_t bytes, void* stream, ladine_encoder** out);
+/* dimensions of a packed object (what a wrapper needs after an import):
+ * member  -> dims_out[6] = {feature_dim, num_classes, n_steps, guidance, precision, device}
+ * encoder -> dims_out[4] = {data_dim, hidden_dim, feature_dim, device} */
+int ladine_member_dims(const ladine_member* m, int32_t dims_out[6]);
+int ladine_encoder_dims(const ladine_encoder* enc, int32_t dims_out[4]);
 
 /* padded feature dim and padded class count used by the packed layout */
 int ladine_member_fpad(const ladine_member* m);

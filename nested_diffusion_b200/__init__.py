@@ -7,7 +7,8 @@ plus the batched entry points the 100-call loop collapses into (ensemble.NestedE
 ensemble.sample_ensemble) and the ensemble statistics (stats).
 """
 from . import diffusion_utils, latent_model, schedule, stats  # noqa: F401
-from .engine import PackedMember, fill_noise, packed_member_of, sample_chains  # noqa: F401
+from .engine import (PackedEncoder, PackedMember, PackedModel, fill_noise, packed_member_of,  # noqa: F401
+                     sample_chains)
 from .ensemble import (NestedEnsemble, gather_image_shards, sample_ensemble, shard_bounds,  # noqa: F401
                        weighted_bounds)
 from .latent_model import ConditionalLinear, ConditionalModel  # noqa: F401

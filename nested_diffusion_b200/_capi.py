@@ -76,6 +76,14 @@ SYMBOLS = {
     "ladine_encode": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                 C.c_void_p]),
     "ladine_last_encoder_launches": (C.c_int64, [C.c_void_p]),
+    "ladine_member_image_bytes": (C.c_uint64, [C.c_void_p]),
+    "ladine_member_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "ladine_member_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ladine_encoder_image_bytes": (C.c_uint64, [C.c_void_p]),
+    "ladine_encoder_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "ladine_encoder_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ladine_member_dims": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "ladine_encoder_dims": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "ladine_debug_plan": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int32)]),
     "ladine_debug_layer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,

@@ -259,6 +259,92 @@ cudaError_t order_after_previous_call(ladine_handle* h, cudaStream_t st) {
 void mark_call_done(ladine_handle* h, cudaStream_t st) {
   if (h->ev_done) cudaEventRecord(h->ev_done, st);
 }
+// ---- packed images (on-disk cache of packed members / encoders) ----
+uint64_t image_checksum(const void* p, size_t n) {
+  // four interleaved multiply-xor lanes over 64-bit words (memory-bound on the host), tail bytes folded in at the end
+  const uint64_t kMul = 0x9E3779B97F4A7C15ull;
+  uint64_t lane[4] = {0x243F6A8885A308D3ull, 0x13198A2E03707344ull, 0xA4093822299F31D0ull, 0x082EFA98EC4E6C89ull};
+  const unsigned char* b = static_cast<const unsigned char*>(p);
+  const size_t words = n / 8;
+  size_t i = 0;
+  for (; i + 4 <= words; i += 4) {
+    uint64_t w[4];
+    std::memcpy(w, b + 8 * i, 32);
+    for (int l = 0; l < 4; ++l) lane[l] = (lane[l] ^ w[l]) * kMul;
+  }
+  uint64_t acc = lane[0];
+  for (int l = 1; l < 4; ++l) acc = (acc ^ (lane[l] >> 29) ^ lane[l]) * kMul;
+  for (size_t j = 8 * i; j < n; ++j) acc = (acc ^ b[j]) * kMul;
+  return acc ^ (uint64_t)n;
+}
+
+uint64_t image_export(const char* magic, const int32_t* dims, int n_dims, const std::vector<ImageSection>& secs,
+                      void* host_dst, uint64_t cap, cudaStream_t st, cudaError_t* status) {
+  *status = cudaSuccess;
+  uint64_t payload = 0;
+  for (const auto& s : secs) payload += (s.bytes + 15) / 16 * 16;
+  const uint64_t total = kImageHeaderBytes + payload;
+  if (!host_dst || cap < total) return host_dst ? 0 : total;
+  unsigned char* dst = static_cast<unsigned char*>(host_dst);
+  std::memset(dst, 0, kImageHeaderBytes);
+  uint64_t off = kImageHeaderBytes;
+  for (const auto& s : secs) {
+    const uint64_t padded = (s.bytes + 15) / 16 * 16;
+    if (padded != s.bytes) std::memset(dst + off + s.bytes, 0, padded - s.bytes);
+    cudaError_t e = cudaMemcpyAsync(dst + off, *s.dev, s.bytes, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { *status = e; return 0; }
+    off += padded;
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { *status = e; return 0; }
+  ImageHeader hd{};
+  std::memcpy(hd.magic, magic, std::min<size_t>(7, std::strlen(magic)));
+  hd.abi = LADINE_ABI_VERSION;
+  hd.layout = kImageLayout;
+  for (int i = 0; i < n_dims && i < 20; ++i) hd.dims[i] = dims[i];
+  hd.payload_bytes = payload;
+  hd.checksum = image_checksum(dst + kImageHeaderBytes, payload);
+  std::memcpy(dst, &hd, sizeof hd);
+  return total;
+}
+
+const char* image_check(const void* host_src, uint64_t bytes, const char* magic, const ImageHeader** hdr_out) {
+  if (!host_src || bytes < kImageHeaderBytes) return "image shorter than its header";
+  const ImageHeader* hd = static_cast<const ImageHeader*>(host_src);
+  if ((reinterpret_cast<uintptr_t>(host_src) & 7) != 0) return "image buffer must be 8-byte aligned";
+  if (std::strncmp(hd->magic, magic, 8) != 0) return "not a packed image of this kind (magic mismatch)";
+  if (hd->abi != LADINE_ABI_VERSION || hd->layout != kImageLayout)
+    return "packed image was written by a different library version / packed layout: re-pack from the checkpoint";
+  if (hd->payload_bytes != bytes - kImageHeaderBytes) return "packed image is truncated or has trailing bytes";
+  if (image_checksum(static_cast<const unsigned char*>(host_src) + kImageHeaderBytes, hd->payload_bytes) != hd->checksum)
+    return "packed image checksum mismatch (corrupt file)";
+  *hdr_out = hd;
+  return nullptr;
+}
+
+cudaError_t image_import(const void* host_src, const std::vector<ImageSection>& secs, cudaStream_t st) {
+  const unsigned char* src = static_cast<const unsigned char*>(host_src);
+  uint64_t off = kImageHeaderBytes;
+  cudaError_t e = cudaSuccess;
+  size_t done = 0;
+  for (; done < secs.size() && e == cudaSuccess; ++done) {
+    const auto& s = secs[done];
+    *s.dev = nullptr;
+    e = cudaMalloc(s.dev, s.bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(*s.dev, src + off, s.bytes, cudaMemcpyHostToDevice, st);
+    off += (s.bytes + 15) / 16 * 16;
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // the host buffer is the caller's again on return
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    for (size_t i = 0; i < done; ++i) {
+      cudaFree(*secs[i].dev);
+      *secs[i].dev = nullptr;
+    }
+  }
+  return e;
+}
+
 cudaError_t launch_guidance_u(const ladine_member* const* members, int K, int N, const float* y0hat, float* u,
                               cudaStream_t st) {
   GuidanceParams p{};
@@ -331,6 +417,12 @@ uint64_t ladine_member_bytes(const ladine_member* m) { return m ? m->bytes : 0; 
 int ladine_member_precision(const ladine_member* m) { return m ? m->precision : LADINE_ERR_INVALID; }
 int ladine_member_fpad(const ladine_member* m) { return m ? m->Fp : LADINE_ERR_INVALID; }
 int ladine_member_cpad(const ladine_member* m) { return m ? m->Cp : LADINE_ERR_INVALID; }
+int ladine_member_dims(const ladine_member* m, int32_t dims_out[6]) {
+  if (!m || !dims_out) return LADINE_ERR_INVALID;
+  const int32_t d[6] = {m->F, m->C, m->T, m->guidance, m->precision, m->device};
+  std::memcpy(dims_out, d, sizeof d);
+  return LADINE_OK;
+}
 
 int ladine_pack_member(ladine_handle* h, const ladine_member_desc* d, void* stream, ladine_member** out) {
   if (!h) return LADINE_ERR_INVALID;
@@ -448,6 +540,86 @@ int ladine_free_member(ladine_handle* h, ladine_member* m) {
   free_member_buffers(m);
   delete m;
   (void)h;
+  return LADINE_OK;
+}
+
+// ---- packed-member images (checkpoint ingestion with a cache that skips re-packing) ----
+static std::vector<ImageSection> member_sections(ladine_member* m) {
+  const size_t tf = (size_t)m->T * m->Fp * sizeof(float), fc = (size_t)m->Fp * m->Cp * sizeof(float);
+  const size_t ff = (size_t)m->Fp * m->Fp;
+  std::vector<ImageSection> s;
+  for (int l = 0; l < 3; ++l) {
+    s.push_back({reinterpret_cast<void**>(&m->A[l]), tf});
+    s.push_back({reinterpret_cast<void**>(&m->Cc[l]), tf});
+  }
+  s.push_back({reinterpret_cast<void**>(&m->W1y), fc});
+  s.push_back({reinterpret_cast<void**>(&m->W1g), fc});
+  s.push_back({reinterpret_cast<void**>(&m->W4), fc});
+  s.push_back({reinterpret_cast<void**>(&m->b4), (size_t)m->Cp * sizeof(float)});
+  if (m->precision != LADINE_PREC_FP32) {
+    s.push_back({&m->W2h, ff * 2 * (m->split ? 2 : 1)});
+    s.push_back({&m->W3h, ff * 2 * (m->split ? 2 : 1)});
+    if (m->split) s.push_back({reinterpret_cast<void**>(&m->wscale), 8 * sizeof(float)});
+  } else {
+    s.push_back({reinterpret_cast<void**>(&m->W2t), ff * sizeof(float)});
+    s.push_back({reinterpret_cast<void**>(&m->W3t), ff * sizeof(float)});
+  }
+  return s;
+}
+
+uint64_t ladine_member_image_bytes(const ladine_member* m) {
+  if (!m) return 0;
+  uint64_t total = kImageHeaderBytes;
+  for (const auto& s : member_sections(const_cast<ladine_member*>(m))) total += (s.bytes + 15) / 16 * 16;
+  return total;
+}
+
+int ladine_member_export(ladine_handle* h, const ladine_member* m, void* host_dst, uint64_t capacity, void* stream) {
+  if (!h) return LADINE_ERR_INVALID;
+  if (!m || !host_dst) return fail(h, LADINE_ERR_INVALID, "null member or destination");
+  if (capacity < ladine_member_image_bytes(m)) return fail(h, LADINE_ERR_INVALID, "destination smaller than ladine_member_image_bytes");
+  DeviceGuard guard(m->device);
+  const int32_t dims[8] = {m->F, m->Fp, m->C, m->Cp, m->T, m->guidance, m->precision, m->split};
+  cudaError_t e = cudaSuccess;
+  const uint64_t n = image_export("LADINEM", dims, 8, member_sections(const_cast<ladine_member*>(m)), host_dst, capacity,
+                                  static_cast<cudaStream_t>(stream), &e);
+  if (e != cudaSuccess || n == 0) return fail_cuda(h, e, "member export");
+  return LADINE_OK;
+}
+
+int ladine_member_import(ladine_handle* h, const void* host_src, uint64_t bytes, void* stream, ladine_member** out) {
+  if (!h) return LADINE_ERR_INVALID;
+  if (!out) return fail(h, LADINE_ERR_INVALID, "null output");
+  *out = nullptr;
+  const ImageHeader* hd = nullptr;
+  if (const char* why = image_check(host_src, bytes, "LADINEM", &hd)) return fail(h, LADINE_ERR_INVALID, why);
+  ladine_member* m = new (std::nothrow) ladine_member();
+  if (!m) return fail(h, LADINE_ERR_NOMEM, "host allocation failed");
+  m->F = hd->dims[0]; m->Fp = hd->dims[1]; m->C = hd->dims[2]; m->Cp = hd->dims[3]; m->T = hd->dims[4];
+  m->guidance = hd->dims[5]; m->precision = hd->dims[6]; m->split = hd->dims[7];
+  m->device = h->device;
+  const bool tensor = m->precision != LADINE_PREC_FP32;
+  const bool sane = m->F >= 1 && m->C >= 1 && m->C <= LADINE_MAX_CLASSES && m->T >= 1 && m->Cp == cpad_of(m->C) &&
+                    (m->precision == LADINE_PREC_FP32 || m->precision == LADINE_PREC_FP16 ||
+                     m->precision == LADINE_PREC_BF16 || m->precision == LADINE_PREC_FP32X) &&
+                    m->Fp == (int)align_up(m->F, tensor ? 256 : 32) && m->split == (m->precision == LADINE_PREC_FP32X ? 1 : 0) &&
+                    (m->precision != LADINE_PREC_FP32 || m->F <= 128);
+  auto secs = member_sections(m);
+  uint64_t payload = 0;
+  for (const auto& s : secs) payload += (s.bytes + 15) / 16 * 16;
+  if (!sane || payload != hd->payload_bytes) {
+    delete m;
+    return fail(h, LADINE_ERR_INVALID, "packed member image: inconsistent dimensions");
+  }
+  DeviceGuard guard(h->device);
+  cudaError_t e = image_import(host_src, secs, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    delete m;
+    return e == cudaErrorMemoryAllocation ? fail(h, LADINE_ERR_NOMEM, "device allocation failed while importing a member")
+                                          : fail_cuda(h, e, "member import");
+  }
+  for (const auto& s : secs) m->bytes += s.bytes;
+  *out = m;
   return LADINE_OK;
 }
 

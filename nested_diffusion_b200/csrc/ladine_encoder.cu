@@ -17,6 +17,7 @@
 // softplus.  Layers 2 and 3 (4096 x 4096) reuse the same two kernels.
 #include <algorithm>
 #include <atomic>
+#include <cstring>
 
 #include "ladine_split.cuh"
 #include "ladine_tensor.cuh"
@@ -306,6 +307,87 @@ int ladine_free_encoder(ladine_handle* h, ladine_encoder* e) {
 }
 
 uint64_t ladine_encoder_bytes(const ladine_encoder* e) { return e ? e->bytes : 0; }
+int ladine_encoder_dims(const ladine_encoder* e, int32_t dims_out[4]) {
+  if (!e || !dims_out) return LADINE_ERR_INVALID;
+  const int32_t d[4] = {e->Dx, e->H, e->F, e->device};
+  std::memcpy(dims_out, d, sizeof d);
+  return LADINE_OK;
+}
+
+// ---- packed-encoder images ----
+static std::vector<ImageSection> encoder_sections(ladine_encoder* e) {
+  std::vector<ImageSection> s;
+  s.push_back({reinterpret_cast<void**>(&e->wscale), 16 * sizeof(float)});
+  for (int l = 0; l < 3; ++l) {
+    s.push_back({reinterpret_cast<void**>(&e->Ws[l]), (size_t)e->Np[l] * 2 * e->Kp[l] * sizeof(__half)});
+    for (int v = 0; v < 5; ++v) s.push_back({reinterpret_cast<void**>(&e->vec[l][v]), (size_t)e->Nout[l] * sizeof(float)});
+  }
+  return s;
+}
+
+uint64_t ladine_encoder_image_bytes(const ladine_encoder* e) {
+  if (!e) return 0;
+  uint64_t total = kImageHeaderBytes;
+  for (const auto& s : encoder_sections(const_cast<ladine_encoder*>(e))) total += (s.bytes + 15) / 16 * 16;
+  return total;
+}
+
+int ladine_encoder_export(ladine_handle* h, const ladine_encoder* e, void* host_dst, uint64_t capacity, void* stream) {
+  if (!h) return LADINE_ERR_INVALID;
+  if (!e || !host_dst) return efail(h, LADINE_ERR_INVALID, "null encoder or destination");
+  if (capacity < ladine_encoder_image_bytes(e))
+    return efail(h, LADINE_ERR_INVALID, "destination smaller than ladine_encoder_image_bytes");
+  EncDeviceGuard guard(e->device);
+  int32_t eps_bits;
+  std::memcpy(&eps_bits, &e->eps, 4);
+  const int32_t dims[4] = {e->Dx, e->H, e->F, eps_bits};
+  cudaError_t ce = cudaSuccess;
+  const uint64_t n = image_export("LADINEE", dims, 4, encoder_sections(const_cast<ladine_encoder*>(e)), host_dst, capacity,
+                                  static_cast<cudaStream_t>(stream), &ce);
+  if (ce != cudaSuccess || n == 0) return efail(h, LADINE_ERR_CUDA, std::string("encoder export: ") + cudaGetErrorString(ce));
+  return LADINE_OK;
+}
+
+int ladine_encoder_import(ladine_handle* h, const void* host_src, uint64_t bytes, void* stream, ladine_encoder** out) {
+  if (!h) return LADINE_ERR_INVALID;
+  if (!out) return efail(h, LADINE_ERR_INVALID, "null output");
+  *out = nullptr;
+  const ImageHeader* hd = nullptr;
+  if (const char* why = image_check(host_src, bytes, "LADINEE", &hd)) return efail(h, LADINE_ERR_INVALID, why);
+  ladine_encoder* e = new (std::nothrow) ladine_encoder();
+  if (!e) return efail(h, LADINE_ERR_NOMEM, "host allocation failed");
+  e->Dx = hd->dims[0]; e->H = hd->dims[1]; e->F = hd->dims[2];
+  std::memcpy(&e->eps, &hd->dims[3], 4);
+  e->device = h->device;
+  if (e->Dx < 1 || e->H < 1 || e->F < 1) {
+    delete e;
+    return efail(h, LADINE_ERR_INVALID, "packed encoder image: inconsistent dimensions");
+  }
+  const int K[3] = {e->Dx, e->H, e->H};
+  const int N[3] = {e->H, e->H, e->F};
+  for (int l = 0; l < 3; ++l) {
+    e->Kp[l] = (int)up(K[l], EBK);
+    e->Np[l] = (int)up(N[l], EBN);
+    e->Nout[l] = N[l];
+  }
+  auto secs = encoder_sections(e);
+  uint64_t payload = 0;
+  for (const auto& s : secs) payload += (s.bytes + 15) / 16 * 16;
+  if (payload != hd->payload_bytes) {
+    delete e;
+    return efail(h, LADINE_ERR_INVALID, "packed encoder image: inconsistent dimensions");
+  }
+  EncDeviceGuard guard(h->device);
+  cudaError_t ce = image_import(host_src, secs, static_cast<cudaStream_t>(stream));
+  if (ce != cudaSuccess) {
+    delete e;
+    return efail(h, ce == cudaErrorMemoryAllocation ? LADINE_ERR_NOMEM : LADINE_ERR_CUDA,
+                 std::string("encoder import: ") + cudaGetErrorString(ce));
+  }
+  for (int l = 0; l < 3; ++l) e->bytes += (size_t)e->Np[l] * 2 * e->Kp[l] * sizeof(__half) + 5ull * N[l] * sizeof(float);
+  *out = e;
+  return LADINE_OK;
+}
 
 int ladine_encode(ladine_handle* h, const ladine_encoder* const* encoders, int32_t K, const float* x, int32_t N,
                   float* xf_out, void* stream) {

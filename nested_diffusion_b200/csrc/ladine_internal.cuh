@@ -125,6 +125,34 @@ cudaError_t launch_persistent_chain(ladine_handle* h, const ladine_member* const
 cudaError_t order_after_previous_call(ladine_handle* h, cudaStream_t st);
 void mark_call_done(ladine_handle* h, cudaStream_t st);
 
+// ---- packed images: a packed member / encoder serialised for an on-disk cache ----
+// 128-byte header + the packed device buffers back to back in declaration order.  `layout` changes whenever a packing
+// kernel or a buffer layout changes, so a stale file is refused instead of mis-read.
+constexpr uint32_t kImageLayout = 1;
+struct ImageHeader {
+  char magic[8];            // "LADINEM" / "LADINEE"
+  uint32_t abi;             // LADINE_ABI_VERSION of the writer
+  uint32_t layout;          // kImageLayout
+  int32_t dims[20];         // the scalar fields of the packed object (see image_export / image_import)
+  uint64_t payload_bytes;   // bytes after the header
+  uint64_t checksum;        // image_checksum(payload)
+  uint64_t reserved;
+};
+static_assert(sizeof(ImageHeader) == 120, "ImageHeader layout");
+constexpr size_t kImageHeaderBytes = 128;   // the header padded so that the payload stays 16-byte aligned
+struct ImageSection {
+  void** dev;      // address of the owning pointer inside the packed object
+  size_t bytes;
+};
+uint64_t image_checksum(const void* p, size_t n);
+// D2H of every section behind a header into host_dst (synchronises `st`); returns the bytes written or 0 (cap too small)
+uint64_t image_export(const char* magic, const int32_t* dims, int n_dims, const std::vector<ImageSection>& secs,
+                      void* host_dst, uint64_t cap, cudaStream_t st, cudaError_t* status);
+// header checks of an image; on success *hdr_out points into host_src
+const char* image_check(const void* host_src, uint64_t bytes, const char* magic, const ImageHeader** hdr_out);
+// cudaMalloc + H2D of every section (synchronises `st`); on failure everything allocated here is released
+cudaError_t image_import(const void* host_src, const std::vector<ImageSection>& secs, cudaStream_t st);
+
 // ---- shared small kernels (ladine_api.cu) ----
 cudaError_t launch_guidance_u(const ladine_member* const* members, int K, int N, const float* y0hat, float* u,
                               cudaStream_t st);

@@ -28,6 +28,30 @@ def _device_index(device: torch.device) -> int:
     return device.index if device.index is not None else torch.cuda.current_device()
 
 
+def _export_image(obj, kind: str) -> torch.Tensor:
+    lib = _capi.load()
+    n = int(getattr(lib, f"ladine_{kind}_image_bytes")(obj.ptr))
+    buf = torch.empty(n, dtype=torch.uint8).pin_memory()
+    with torch.cuda.device(obj.device_index), _capi.call_lock(obj.device_index):
+        stream = torch.cuda.current_stream().cuda_stream
+        _capi.check(obj._h, getattr(lib, f"ladine_{kind}_export")(obj._h, obj.ptr, C.c_void_p(buf.data_ptr()), n,
+                                                                   C.c_void_p(stream)))
+    return buf
+
+
+def _import_image(image: torch.Tensor, device_index: int, kind: str) -> int:
+    if image.device.type != "cpu" or image.dtype != torch.uint8 or image.dim() != 1 or not image.is_contiguous():
+        raise ValueError("a packed image is a contiguous 1-D HOST uint8 tensor (export_image / torch.from_file)")
+    lib = _capi.load()
+    h = _capi.handle(device_index)
+    out = C.c_void_p()
+    with torch.cuda.device(device_index), _capi.call_lock(device_index):
+        stream = torch.cuda.current_stream().cuda_stream
+        _capi.check(h, getattr(lib, f"ladine_{kind}_import")(h, C.c_void_p(image.data_ptr()), image.numel(),
+                                                             C.c_void_p(stream), C.byref(out)))
+    return out.value
+
+
 class PackedMember:
     """One ensemble member folded and re-laid-out on the device (ladine_pack_member)."""
 
@@ -93,7 +117,15 @@ class PackedMember:
             _capi.check(self._h, lib.ladine_pack_member(self._h, C.byref(d), C.c_void_p(stream), C.byref(out)))
             torch.cuda.current_stream().synchronize()  # sources may now be released
         del keep
-        self._ptr = out.value
+        self._adopt(out.value)
+
+    def _adopt(self, ptr: int) -> None:
+        """Take ownership of a ``ladine_member*`` and mirror its dimensions."""
+        lib = _capi.load()
+        self._ptr = ptr
+        dims = (C.c_int32 * 6)()
+        lib.ladine_member_dims(self._ptr, dims)
+        self.F, self.C, self.T, self.guidance = int(dims[0]), int(dims[1]), int(dims[2]), bool(dims[3])
         self.precision = _capi.PREC_NAME[lib.ladine_member_precision(self._ptr)]
         self.Fp = lib.ladine_member_fpad(self._ptr)
         self.Cp = lib.ladine_member_cpad(self._ptr)
@@ -103,6 +135,22 @@ class PackedMember:
     @property
     def ptr(self) -> int:
         return self._ptr
+
+    # -- packed images (ladine_member_export / ladine_member_import): the on-disk cache of runner.load_noise_estimators --
+    def export_image(self) -> torch.Tensor:
+        """The packed member as a pinned HOST uint8 tensor (header + packed buffers)."""
+        return _export_image(self, "member")
+
+    @classmethod
+    def from_image(cls, image: torch.Tensor, device) -> "PackedMember":
+        """Restore a packed member from ``export_image()`` bytes on ``device`` (raises LadineError for a stale, truncated
+        or corrupt image: pack from the checkpoint again)."""
+        self = cls.__new__(cls)
+        self.device_index = _device_index(torch.device(device))
+        self.device = torch.device("cuda", self.device_index)
+        self._h = _capi.handle(self.device_index)
+        self._adopt(_import_image(image, self.device_index, "member"))
+        return self
 
 
 # ------------------------------------------------------------------------------------------------
@@ -163,6 +211,10 @@ def packed_member_of(model, precision: str = "auto") -> PackedMember:
     """Pack ``model`` (a ConditionalModel-shaped nn.Module) once and reuse it across calls (see the cache rules above)."""
     if isinstance(model, PackedMember):
         return model
+    if isinstance(model, PackedModel):
+        if precision not in ("auto", model.member.precision):
+            raise ValueError(f"this PackedModel was packed as {model.member.precision!r}, not {precision!r}")
+        return model.member
     tensors = _select(model, True)
     hit = _PACK_CACHE.get(model)
     if hit is not None and hit.valid_for(tensors, precision):
@@ -279,13 +331,56 @@ class PackedEncoder:
             _capi.check(self._h, lib.ladine_pack_encoder(self._h, C.byref(d), C.c_void_p(stream), C.byref(out)))
             torch.cuda.current_stream().synchronize()
         del keep
-        self._ptr = out.value
+        self._adopt(out.value)
+
+    def _adopt(self, ptr: int) -> None:
+        lib = _capi.load()
+        self._ptr = ptr
+        dims = (C.c_int32 * 4)()
+        lib.ladine_encoder_dims(self._ptr, dims)
+        self.Dx, self.H, self.F = int(dims[0]), int(dims[1]), int(dims[2])
         self.nbytes = int(lib.ladine_encoder_bytes(self._ptr))
         self._finalizer = weakref.finalize(self, lib.ladine_free_encoder, self._h, self._ptr)
 
     @property
     def ptr(self) -> int:
         return self._ptr
+
+    def export_image(self) -> torch.Tensor:
+        """The packed encoder as a pinned HOST uint8 tensor (ladine_encoder_export)."""
+        return _export_image(self, "encoder")
+
+    @classmethod
+    def from_image(cls, image: torch.Tensor, device) -> "PackedEncoder":
+        self = cls.__new__(cls)
+        self.device_index = _device_index(torch.device(device))
+        self._h = _capi.handle(self.device_index)
+        self._adopt(_import_image(image, self.device_index, "encoder"))
+        return self
+
+
+class PackedModel:
+    """A member that exists ONLY in packed form: the trunk (``PackedMember``) and the 'linear' encoder (``PackedEncoder``)
+    restored from an on-disk image, without the 2.59 GiB nn.Module behind them.  Accepted wherever the batched API takes a
+    model (``NestedEnsemble``, ``sample_ensemble``, ``encode_members``, the runner shim); it is always in eval mode."""
+
+    training = False
+
+    def __init__(self, member: PackedMember, encoder: "PackedEncoder"):
+        if member.device_index != encoder.device_index:
+            raise ValueError("packed trunk and packed encoder live on different devices")
+        if member.F != encoder.F:
+            raise ValueError(f"encoder feature_dim {encoder.F} != trunk feature_dim {member.F}")
+        self.member, self.encoder = member, encoder
+        self.device = member.device
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        if torch.device(device).type != "cuda" or _device_index(torch.device(device)) != self.member.device_index:
+            raise NotImplementedError("a PackedModel stays on the GPU it was restored on (no CPU copy exists)")
+        return self
 
 
 _ENC_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
@@ -294,6 +389,8 @@ _ENC_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 def packed_encoder_of(model) -> Optional[PackedEncoder]:
     """Pack ``model``'s encoder once (re-packed when an encoder / norm parameter changes); None when the kernel does
     not cover this encoder (other archs, CPU parameters, train mode)."""
+    if isinstance(model, PackedModel):
+        return model.encoder
     if getattr(model, "training", False) or _kernel_encoder_layers(model) is None:
         return None
     tensors = _select(model, False)
@@ -330,6 +427,9 @@ def encode_members(models: Sequence, x: torch.Tensor, mode: str = "auto") -> tor
             return out
         if mode == "kernel":
             raise NotImplementedError("ladine_encode does not cover these encoders / this input (see PackedEncoder)")
+    if any(isinstance(m, PackedModel) for m in models):
+        raise NotImplementedError("a PackedModel has no PyTorch encoder to fall back to: pass CUDA images [N, data_dim] "
+                                  "on its device, and do not mix it with members of other encoder shapes")
     tmode = "fp32" if mode in ("auto", "kernel", "torch") else mode
     return torch.stack([_encode_torch(m, x, tmode) for m in models])
 

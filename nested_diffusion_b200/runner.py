@@ -16,6 +16,7 @@ stays PyTorch (north_star) and lives outside this package.
 from __future__ import annotations
 
 import logging
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Dict, Iterable, List, Optional, Sequence
 
@@ -35,20 +36,90 @@ def temperature_for(dataset: str) -> float:
     raise NotImplementedError(f"no scaling temperature defined for dataset {dataset!r}")
 
 
-def load_noise_estimators(config, ckpt_paths: Sequence[str], device, guidance: Optional[bool] = None) -> List:
+def _content_key(path: str, precision: str) -> str:
+    """blake2b of the checkpoint file's CONTENT (not its name or mtime) + what the packed form depends on."""
+    import hashlib
+
+    from . import _capi
+
+    hh = hashlib.blake2b(digest_size=16)
+    with open(path, "rb") as f:
+        while True:
+            chunk = f.read(1 << 24)
+            if not chunk:
+                break
+            hh.update(chunk)
+    return f"{hh.hexdigest()}-{precision}-abi{_capi.load().ladine_version()}"
+
+
+def _read_image(path: str) -> torch.Tensor:
+    n = os.path.getsize(path)
+    buf = torch.empty(n, dtype=torch.uint8)
+    with open(path, "rb") as f:
+        got = f.readinto(memoryview(buf.numpy()))
+    if got != n:
+        raise OSError(f"short read of {path}")
+    return buf
+
+
+def _write_image(path: str, image: torch.Tensor) -> None:
+    tmp = f"{path}.tmp{os.getpid()}"
+    with open(tmp, "wb") as f:
+        f.write(memoryview(image.numpy()))
+    os.replace(tmp, path)   # atomic: a concurrent reader sees the old file or the complete new one
+
+
+def load_noise_estimators(config, ckpt_paths: Sequence[str], device, guidance: Optional[bool] = None,
+                          cache_dir: Optional[str] = None, precision: str = "auto") -> List:
     """Build one ConditionalModel per checkpoint and load ``state['noise_estimator']`` into it
-    (classification_train_separately.py:684-697), directly on ``device`` and in eval mode."""
+    (classification_train_separately.py:684-697), directly on ``device`` and in eval mode.
+
+    ``cache_dir``: keep the PACKED form of every checkpoint on disk, keyed by a hash of the checkpoint
+    file's content, the packing precision and the library's ABI version.  A hit restores the packed trunk and the
+    packed encoder straight into device memory (``ladine_member_import`` / ``ladine_encoder_import``) and skips building
+    the 2.59 GiB module, ``load_state_dict`` and the packing kernels; a miss packs as usual and writes the two images.
+    With a cache the members are returned as ``engine.PackedModel`` objects (packed form only -- the FP32 module is
+    released), which ``NestedEnsemble`` / ``NestedDiffusionTester`` accept like modules.  A stale, truncated or corrupt
+    image is ignored and rebuilt from the checkpoint.  Encoders the kernel does not cover are not cached (the module
+    is returned)."""
+    from . import engine
+    from ._capi import LadineError
     from .latent_model import ConditionalModel
 
     if guidance is None:
         guidance = bool(config.diffusion.include_guidance)
+    if cache_dir is not None:
+        os.makedirs(cache_dir, exist_ok=True)
     members = []
     for path in ckpt_paths:
+        files = None
+        if cache_dir is not None:
+            key = _content_key(path, precision)
+            files = [os.path.join(cache_dir, f"{key}.{kind}.ladine") for kind in ("member", "encoder")]
+            if all(os.path.exists(f) for f in files):
+                try:
+                    pm = engine.PackedMember.from_image(_read_image(files[0]), device)
+                    pe = engine.PackedEncoder.from_image(_read_image(files[1]), device)
+                    if pm.guidance != bool(guidance):
+                        raise ValueError("cached member was packed with a different guidance setting")
+                    members.append(engine.PackedModel(pm, pe))
+                    continue
+                except (LadineError, OSError, ValueError) as e:
+                    logging.warning(f"packed cache entry for {path} ignored ({e}); re-packing from the checkpoint")
         state = torch.load(path, map_location="cpu")
         sd = state["noise_estimator"] if isinstance(state, dict) and "noise_estimator" in state else state
         m = ConditionalModel(config, guidance=guidance)
         m.load_state_dict(sd)
-        members.append(m.to(device).eval())
+        m = m.to(device).eval()
+        if files is not None:
+            pe = engine.packed_encoder_of(m)
+            if pe is not None:
+                pm = engine.packed_member_of(m, precision)
+                _write_image(files[0], pm.export_image())
+                _write_image(files[1], pe.export_image())
+                members.append(engine.PackedModel(pm, pe))
+                continue
+        members.append(m)
     return members
 
 

@@ -526,6 +526,106 @@ def test_pack_caches_survive_the_runners_device_shuttle():
     assert not torch.equal(run(), second)
 
 
+@pytest.mark.parametrize("name,prec", [("tc_f256_t200", "fp16"), ("tc_f256_t200", "fp32x"), ("small_f128_t50", "fp32")])
+def test_packed_images_round_trip_and_refuse_damage(name, prec):
+    """a packed member / encoder exported to host bytes and imported again samples BITWISE the same; a
+    flipped byte, a truncated buffer, an image of the other kind and an image of another layout version are refused."""
+    import nested_diffusion_b200 as nd
+    from nested_diffusion_b200 import engine
+    from nested_diffusion_b200._capi import LadineError
+    from nested_diffusion_b200.schedule import coef_table
+
+    fx = ChainFixture(name)
+    m = fx.meta
+    sd, x, yhat, noise, alphas, omabs = fx.materialize()
+    model = make_model(m, sd)
+    pm, pe = engine.packed_member_of(model, prec), engine.packed_encoder_of(model)
+    img_m, img_e = pm.export_image(), pe.export_image()
+    pm2, pe2 = nd.PackedMember.from_image(img_m.clone(), "cuda"), nd.PackedEncoder.from_image(img_e.clone(), "cuda")
+    assert (pm2.F, pm2.C, pm2.T, pm2.guidance, pm2.precision, pm2.Fp, pm2.nbytes) == \
+           (pm.F, pm.C, pm.T, pm.guidance, pm.precision, pm.Fp, pm.nbytes)
+    assert (pe2.Dx, pe2.H, pe2.F, pe2.nbytes) == (pe.Dx, pe.H, pe.F, pe.nbytes)
+    assert torch.equal(pm2.export_image(), img_m) and torch.equal(pe2.export_image(), img_e)
+
+    packed = nd.PackedModel(pm2, pe2)
+    xc, yc = x.cuda(), yhat.cuda()
+    coef = coef_table(alphas, omabs, m["T"])
+    nz = noise[: m["T"]].reshape(1, 1, m["T"], *yhat.shape).cuda()
+    xf_a, xf_b = engine.encode_members([model], xc), engine.encode_members([packed], xc)
+    assert torch.equal(xf_a, xf_b)
+    ya = nd.sample_chains([pm], xf_a, yc[None], yc[None], coef, 1, noise=nz)["y"]
+    yb = nd.sample_chains([engine.packed_member_of(packed, prec)], xf_b, yc[None], yc[None], coef, 1, noise=nz)["y"]
+    assert torch.equal(ya, yb)
+    assert rel_err(yb[0, 0].cpu(), fx["y0"]) <= TOL[prec]          # and it is still the reference's answer
+    ens = nd.NestedEnsemble([packed], precision=prec)           # the batched API takes the packed-only member
+    yc3 = ens.sample(xc, yc[None], 1, m["T"], alphas, omabs, noise=nz).y0
+    assert torch.equal(yc3, ya)
+    with pytest.raises(ValueError):
+        engine.packed_member_of(packed, "bf16" if prec != "bf16" else "fp16")
+
+    bad = img_m.clone()
+    bad[img_m.numel() // 2] ^= 0x40
+    for damaged in (bad, img_m[:-16].clone(), img_e.clone(), img_m[:64].clone()):
+        with pytest.raises(LadineError):
+            nd.PackedMember.from_image(damaged, "cuda")
+    stale = img_e.clone()
+    stale[12] += 1                                               # header.layout
+    with pytest.raises(LadineError, match="different library version"):
+        nd.PackedEncoder.from_image(stale, "cuda")
+
+
+def test_checkpoint_loader_disk_cache(tmp_path):
+    """runner.load_noise_estimators(cache_dir=...): first run packs and writes the images, second run restores them
+    (bitwise the same samples, no module built), a different checkpoint CONTENT gets its own entry, and a damaged
+    entry is rebuilt from the checkpoint."""
+    import os
+
+    import nested_diffusion_b200 as nd
+    from nested_diffusion_b200 import engine
+    from nested_diffusion_b200.runner import load_noise_estimators
+
+    fx = ChainFixture("tc_f256_t200")
+    m = fx.meta
+    sd, x, yhat, noise, alphas, omabs = fx.materialize()
+    cfg = _ns(diffusion=_ns(timesteps=m["T"], include_guidance=m.get("guidance", True)),
+              data=_ns(num_classes=m["C"], dataset="ChestXRay"),
+              model=_ns(data_dim=m["Dx"], arch="linear", feature_dim=m["F"], hidden_dim=m["H"]))
+    ck = tmp_path / "diffu0_ckpt_best.pth"
+    torch.save({"noise_estimator": sd, "epoch": 3}, ck)
+    cache = tmp_path / "packed"
+    xc, yc = x.cuda(), yhat.cuda()
+    nz = noise[: m["T"]].reshape(1, 1, m["T"], *yhat.shape).cuda()
+
+    def sample(member):
+        return nd.NestedEnsemble([member]).sample(xc, yc[None], 1, m["T"], alphas, omabs, noise=nz).y0
+
+    (plain,) = load_noise_estimators(cfg, [str(ck)], "cuda")
+    want = sample(plain)
+    (first,) = load_noise_estimators(cfg, [str(ck)], "cuda", cache_dir=str(cache))
+    files = sorted(os.listdir(cache))
+    assert isinstance(first, engine.PackedModel) and len(files) == 2 and all(f.endswith(".ladine") for f in files)
+    assert torch.equal(sample(first), want)
+    stamp = {f: os.path.getmtime(cache / f) for f in files}
+    (second,) = load_noise_estimators(cfg, [str(ck)], "cuda", cache_dir=str(cache))
+    assert isinstance(second, engine.PackedModel) and sorted(os.listdir(cache)) == files
+    assert {f: os.path.getmtime(cache / f) for f in files} == stamp          # a hit writes nothing
+    assert torch.equal(sample(second), want)
+    # same name, different content -> different key
+    sd2 = dict(sd)
+    sd2["lin4.bias"] = sd["lin4.bias"] + 0.5
+    torch.save({"noise_estimator": sd2, "epoch": 3}, ck)
+    (third,) = load_noise_estimators(cfg, [str(ck)], "cuda", cache_dir=str(cache))
+    assert len(os.listdir(cache)) == 4 and not torch.equal(sample(third), want)
+    # damaged entry -> rebuilt from the checkpoint
+    victim = [f for f in os.listdir(cache) if f not in files and ".member." in f][0]
+    raw = bytearray((cache / victim).read_bytes())
+    raw[len(raw) // 2] ^= 0x01
+    (cache / victim).write_bytes(bytes(raw))
+    (fourth,) = load_noise_estimators(cfg, [str(ck)], "cuda", cache_dir=str(cache))
+    assert torch.equal(sample(fourth), sample(third))
+    assert (cache / victim).read_bytes() != bytes(raw)
+
+
 def test_empty_and_single_row_batches():
     """Edge shapes of the drop-in: an empty batch is a valid call (the reference's ops are no-ops on [0, C]) and a
     single row must equal the same row sampled inside a larger batch on the same injected noise."""

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libladine.so lacks {name} declared in include/ladine.h"
     assert sorted(_capi.SYMBOLS) == declared, "ctypes binding and header disagree"
-    assert lib.ladine_version() == 2
+    assert lib.ladine_version() == 3
 
 
 def test_struct_sizes_match_header_layout():
@@ -470,3 +470,21 @@ def test_runner_metrics_and_checkpoint_loader(tmp_path):
     assert not loaded.training
     for k, v in src.state_dict().items():
         assert torch.equal(v, loaded.state_dict()[k])
+
+
+def test_packed_cache_key_follows_content_not_name(tmp_path):
+    """the on-disk packed cache is keyed by the checkpoint's CONTENT (+ precision + ABI version)."""
+    from nested_diffusion_b200.runner import _content_key, _read_image, _write_image
+
+    a, b, c = tmp_path / "a.pth", tmp_path / "b.pth", tmp_path / "c.pth"
+    a.write_bytes(b"x" * 100000)
+    b.write_bytes(b"x" * 100000)
+    c.write_bytes(b"x" * 99999 + b"y")
+    assert _content_key(str(a), "fp16") == _content_key(str(b), "fp16")
+    assert _content_key(str(a), "fp16") != _content_key(str(c), "fp16")
+    assert _content_key(str(a), "fp16") != _content_key(str(a), "fp32x")
+    assert _content_key(str(a), "auto").endswith(f"-auto-abi{_capi.load().ladine_version()}")
+    img = torch.arange(1000, dtype=torch.int64).view(torch.uint8)
+    _write_image(str(tmp_path / "i.ladine"), img)
+    assert torch.equal(_read_image(str(tmp_path / "i.ladine")), img)
+    assert [p.name for p in tmp_path.iterdir() if ".tmp" in p.name] == []
