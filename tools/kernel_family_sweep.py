@@ -1,11 +1,13 @@
-"""Small target for `compute-sanitizer --tool memcheck`: every kernel family of libladine at tiny shapes.
+"""Every kernel family of libladine at tiny shapes in one short process (seconds on a B200):
 
-    compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_target.py
+    python tools/kernel_family_sweep.py
 
 Covers: member packing (all precisions), packed-image export / import, the encoder prologue (split-K + finish), the
 tile path in its three geometries (single CTAs, CTA pairs with a half tile, slim tiles) for FP16 / BF16, the FP32X split
-kernels, the FP32 SMEM-resident kernel, the whole-chain persistent kernel, Philox and injected noise, trajectory and
-probability outputs.  Not a parity test (tests/test_gpu_parity.py is): it only checks that the results are finite."""
+kernels, the fused tail + head option, the FP32 SMEM-resident kernel, the whole-chain persistent kernel, Philox and
+injected noise, trajectory and probability outputs.  Meant as the target of a launch list / quick bring-up check on a new
+box (compute-sanitizer is closed on the B200 pool, so memory safety rests on the bounded waits + the parity tests);
+not a parity test (tests/test_gpu_parity.py is): it only checks that the results are finite."""
 import argparse
 import sys
 
@@ -78,4 +80,4 @@ x512 = torch.rand(40, 80, generator=g).to(dev)
 out = engine.sample_chains([engine.packed_member_of(m512, "fp16")], engine.encode_members([m512], x512), yh[:1, :40],
                            yh[:1, :40], coef, 1, seed=8, persistent=True)
 check(f"persistent chain kernel (F=512, 40 chains, launches {engine.last_launches(0)})", out["y"])
-print("sanitize target done")
+print("kernel family sweep done")
