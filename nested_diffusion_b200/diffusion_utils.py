@@ -11,9 +11,17 @@ Differences a caller can observe:
   * keyword-only extras: ``noise=`` injects the N(0,1) draws the reference would take from
     ``torch.randn_like`` (``noise[0]`` -> y_T, ``noise[k]`` -> step t = n_steps - k), ``seed=``
     fixes the counter-based Philox stream, ``precision=`` picks the arithmetic of the packed member.
-    Without either, the seed is drawn from torch's global CPU generator (``torch.manual_seed``).
+    Without either, the seed is drawn from torch's global CPU generator (``torch.manual_seed``);
+  * opt-in ``set_draws_ahead(D)`` / ``LADINE_DRAWS_AHEAD=D``: the runner asks for its posterior draws one call at a
+    time -- ``for trial in range(20): p_sample_loop(same member, same images, ...)``
+    (classification_train_separately.py:770-777).  With draws-ahead the FIRST such call samples D independent chains
+    per row in one batched launch and the next D-1 calls with the very same inputs are served from that batch
+    (see ``p_sample_loop``); the samples are i.i.d. draws of the same posterior either way.
 """
 from __future__ import annotations
+
+import os
+import weakref
 
 import torch
 
@@ -22,6 +30,36 @@ from .schedule import coef_table, make_beta_schedule  # noqa: F401  (re-exported
 
 __all__ = ["make_beta_schedule", "extract", "q_sample", "p_sample", "p_sample_t_1to0", "y_0_reparam",
            "p_sample_loop"]
+
+# ------------------------------------------------------------------------------------------------
+# draws-ahead (opt-in): serve the runner's D sequential p_sample_loop calls from one batched launch
+# ------------------------------------------------------------------------------------------------
+_DRAWS_AHEAD = max(0, int(os.environ.get("LADINE_DRAWS_AHEAD", "0") or 0))
+_AHEAD: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()   # model -> _Ahead
+
+
+def set_draws_ahead(draws: int) -> int:
+    """Enable (``draws`` >= 2) or disable (0 / 1) draws-ahead for ``p_sample_loop``; returns the previous setting.
+    Set it to the runner's ``mc_trials`` (20, classification_train_separately.py:770)."""
+    global _DRAWS_AHEAD
+    prev, _DRAWS_AHEAD = _DRAWS_AHEAD, max(0, int(draws))
+    _AHEAD.clear()
+    return prev
+
+
+def _tensor_key(t: torch.Tensor) -> tuple:
+    return (t.untyped_storage().data_ptr(), t.storage_offset(), tuple(t.shape), tuple(t.stride()), t._version, t.dtype,
+            str(t.device))
+
+
+class _Ahead:
+    """D chains per row sampled by one call, handed out one draw per call while the inputs are provably the same:
+    same storages / views / in-place version counters (strong references are kept, so no address can be recycled for
+    other values), same packed member and same encoder features (both are re-made when a parameter changes)."""
+    __slots__ = ("key", "refs", "samples", "next")
+
+    def __init__(self, key, refs, samples):
+        self.key, self.refs, self.samples, self.next = key, refs, samples, 1
 
 
 def extract(input, t, x):
@@ -72,7 +110,7 @@ def _prepare(model, x, y_0_hat, y_T_mean, output_detach, precision):
 
 def p_sample_loop(model, x, y_0_hat, y_T_mean, n_steps, alphas, one_minus_alphas_bar_sqrt, only_last_sample=False,
                   input_model_original_version=True, output_detach=True, *, noise=None, seed=None, precision="auto",
-                  draws=None, persistent=True):
+                  draws=None, persistent=True, draws_ahead=None):
     """Full reverse chain y_T -> y_0, diffusion_utils.py:133-163.
 
     Returns y_0 ``[B, C]`` when ``only_last_sample`` else the list ``[y_T, ..., y_1, y_0]`` of
@@ -82,12 +120,31 @@ def p_sample_loop(model, x, y_0_hat, y_T_mean, n_steps, alphas, one_minus_alphas
     obtains with D sequential calls (classification_train_separately.py:770-777) -- and returns ``[D, B, C]``
     (needs ``only_last_sample=True``; ``noise``, if given, is ``[D, n_steps, B, C]``).
 
+    ``draws_ahead`` (default: the module setting, ``set_draws_ahead`` / ``LADINE_DRAWS_AHEAD``; off unless set): with
+    D >= 2, a plain call (``only_last_sample=True``, no ``noise`` / ``seed`` / ``draws``) samples D chains per row in one
+    launch, returns the first, and the following D-1 calls with the same model and the very same input tensors
+    (storage, view, in-place version, packed weights, encoder features all unchanged) return the remaining draws without
+    touching the GPU again -- the runner's ``for trial in range(20)`` loop then costs one batched launch per member
+    instead of 20 chains one after the other.  Any change of an input starts a new batch.
+
     ``persistent`` (default True): a call of at most 128 chains at a tensor-core width runs as ONE cooperative launch
     for the whole chain (``engine.sample_chains(persistent=True)``) -- the shape of the runner's own calls (70 images,
     one draw); larger calls use the tile kernels either way."""
     if not input_model_original_version:
         model = model.conditional_model
     pm, xf, yh, mu = _prepare(model, x, y_0_hat, y_T_mean, output_detach, precision)
+    ahead = _DRAWS_AHEAD if draws_ahead is None else max(0, int(draws_ahead))
+    if ahead >= 2 and only_last_sample and noise is None and seed is None and draws is None:
+        key = (id(pm), xf.untyped_storage().data_ptr(), int(n_steps), ahead, bool(persistent)) + tuple(
+            _tensor_key(t) for t in (x, y_0_hat, y_T_mean, alphas, one_minus_alphas_bar_sqrt))
+        st = _AHEAD.get(model)
+        if st is not None and st.key == key and st.next < st.samples.shape[0]:
+            st.next += 1
+            return st.samples[st.next - 1].clone()
+        samples = engine.sample_chains([pm], xf, yh, mu, coef_table(alphas, one_minus_alphas_bar_sqrt, n_steps), ahead,
+                                       seed=engine.fresh_seed(), persistent=persistent)["y"][0]          # [D, B, C]
+        _AHEAD[model] = _Ahead(key, (pm, xf, x, y_0_hat, y_T_mean, alphas, one_minus_alphas_bar_sqrt), samples)
+        return samples[0].clone()
     coef = coef_table(alphas, one_minus_alphas_bar_sqrt, n_steps)
     B, Cc = y_0_hat.shape
     if draws is not None:

@@ -1005,6 +1005,60 @@ def test_fp16_overflow_saturates_instead_of_nan(prec):
     assert rel_err(got, want) <= 2e-2
 
 
+def test_draws_ahead_serves_the_runners_sequential_calls_from_one_batch(monkeypatch):
+    """Opt-in draws-ahead (diffusion_utils.set_draws_ahead / LADINE_DRAWS_AHEAD): the runner's
+    ``for trial in range(mc_trials): p_sample_loop(same member, same images, ...)`` loop
+    (classification_train_separately.py:770-777) is served from ONE batched launch; the D results are exactly the D
+    draws of ``p_sample_loop(draws=D)`` under the same torch seed; any change of an input starts a new batch."""
+    from nested_diffusion_b200 import diffusion_utils as du
+    from nested_diffusion_b200 import engine
+
+    fx = ChainFixture("tc_f256_t200")
+    m = fx.meta
+    sd, x, yhat, _, alphas, omabs = fx.materialize()
+    model = make_model(m, sd)
+    xc, yc, ag, og = x.cuda(), yhat.cuda(), alphas.cuda(), omabs.cuda()
+    D = 4
+    calls = []
+    real = engine.sample_chains
+    monkeypatch.setattr(engine, "sample_chains", lambda *a, **kw: (calls.append(a[5]), real(*a, **kw))[1])
+    call = lambda **kw: du.p_sample_loop(model, xc, yc, yc, m["T"], ag, og, only_last_sample=True, **kw)
+    with torch.no_grad():
+        torch.manual_seed(77)
+        want = call(draws=D)                                   # [D, B, C], one launch
+        assert du.set_draws_ahead(D) == 0
+        try:
+            torch.manual_seed(77)
+            del calls[:]
+            got = [call() for _ in range(D)]
+            assert calls == [D], "the D sequential calls must cost one batched sample_chains call"
+            assert torch.equal(torch.stack(got), want)
+            extra = call()                                     # draw D+1: a new batch with a new seed
+            assert calls == [D, D] and not torch.equal(extra, want[0])
+            yc2 = yc.clone()
+            first = du.p_sample_loop(model, xc, yc2, yc2, m["T"], ag, og, only_last_sample=True)
+            yc2.mul_(0.5).add_(0.25)                           # in-place change of an input: version counter moves
+            torch.manual_seed(5)
+            second = du.p_sample_loop(model, xc, yc2, yc2, m["T"], ag, og, only_last_sample=True)
+            torch.manual_seed(5)
+            fresh = du.p_sample_loop(model, xc, yc2, yc2, m["T"], ag, og, only_last_sample=True, draws=D)[0]
+            assert torch.equal(second, fresh) and not torch.equal(second, first)
+            with torch.no_grad():
+                model.lin4.bias.add_(0.125)                    # a weight changes: re-pack, new batch
+            n = len(calls)
+            third = du.p_sample_loop(model, xc, yc2, yc2, m["T"], ag, og, only_last_sample=True)
+            assert len(calls) == n + 1 and not torch.equal(third, second)
+            # explicit seed / trajectory requests are never served from a batch, and the switch can be overridden per call
+            assert torch.equal(call(seed=3), call(seed=3))
+            assert isinstance(du.p_sample_loop(model, xc, yc, yc, m["T"], ag, og, only_last_sample=False), list)
+            n = len(calls)
+            call(draws_ahead=0)
+            call(draws_ahead=0)
+            assert calls[n:] == [1, 1]
+        finally:
+            du.set_draws_ahead(0)
+
+
 def test_p_sample_loop_draws_extension():
     """draws=D in one launch == D sequential reference-style calls fed the same noise."""
     from nested_diffusion_b200 import diffusion_utils as du

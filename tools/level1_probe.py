@@ -35,7 +35,15 @@ def level2(ens):
     with torch.no_grad():
         return ens.sample(x, yh, draws, T, alphas, omabs, temperature=bench.TEMPERATURE_C2).y0
 
+def level1_ahead():
+    du.set_draws_ahead(draws)
+    try:
+        return level1()
+    finally:
+        du.set_draws_ahead(0)
+
 for name, fn in (("level 1: K x draws sequential p_sample_loop calls", level1),
+                 ("level 1 + draws-ahead (LADINE_DRAWS_AHEAD): the same calls served from one batched launch per member", level1_ahead),
                  ("level 2: one NestedEnsemble.sample call", None)):
     if fn is None:
         ens = nd.NestedEnsemble(models)
