@@ -158,7 +158,8 @@ uint64_t ladine_workspace_bytes(const ladine_handle* h);
  *       joined to the caller's stream) so one group's tail/head kernel hides under another group's GEMMs;
  *   "ctas" (0 auto | 1 | 2 | 3): GEMM tile geometry -- single CTAs (cta_group::1, 128x256 tiles), CTA pairs
  *       (cta_group::2, 256x256 tiles + 2x64-row half tiles) or slim single-CTA 128x128 tiles; auto picks pairs
- *       when the rows pad well and slim tiles when the call is so small that twice as many tiles still fit the
+ *       when the static schedule of pair tiles on sm_count / 2 SM pairs finishes >= 3 % earlier than that of single
+ *       tiles on sm_count SMs, and slim tiles when the call is so small that twice as many tiles still fit the
  *       SMs in one round; all geometries give bit-identical results;
  *   "pair_gain_permille": measured per-tile speed ratio pair/single used by the auto choice (default 1080);
  *   "persist" (0 default | 1): calls of <= 4 members x <= 128 chains run as ONE cooperative launch for the whole chain
@@ -202,6 +203,10 @@ int ladine_debug_layer(ladine_handle* h, const ladine_member* member, int layer,
  * info_out[4] = {units_used, stride, rows_pad, row tiles per member}. */
 int64_t ladine_debug_plan(int32_t K, int32_t rows, int32_t feature_dim_padded, int32_t geometry, int32_t row_major,
                           int32_t units, int32_t* table_out, int64_t cap, int32_t info_out[4]);
+/* Debug/test entry, host only: the GEMM tile geometry (1, 2 or 3, as above) the auto choice takes for a launch group of K
+ * members x `rows` chains each on a device with `sm_count` SMs -- the makespan of the static schedule is compared for
+ * single-CTA tiles and CTA pairs (their tile counts quantise differently on a given SM count). */
+int32_t ladine_debug_geometry(int32_t K, int32_t rows, int32_t feature_dim_padded, int32_t sm_count);
 /*
  * Step-invariant encoder prologue  xf = norm(encoder_x(x))  of the 'linear' ConditionalModel encoder
  * (latent_model.py:126-135: Linear(data_dim, hidden) BN Softplus Linear(hidden, hidden) BN Softplus Linear(hidden, feature);

@@ -84,6 +84,7 @@ SYMBOLS = {
     "ladine_encoder_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ladine_member_dims": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "ladine_encoder_dims": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "ladine_debug_geometry": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "ladine_debug_plan": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int32)]),
     "ladine_debug_layer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,

@@ -960,6 +960,11 @@ int ladine_get_profile(ladine_handle* h, float ms_out[4], int64_t count_out[3]) 
   return LADINE_OK;
 }
 
+int32_t ladine_debug_geometry(int32_t K, int32_t rows, int32_t feature_dim_padded, int32_t sm_count) {
+  if (K < 1 || rows < 1 || feature_dim_padded < 256 || feature_dim_padded % 256 != 0 || sm_count < 2) return LADINE_ERR_INVALID;
+  return ladine::debug_geometry(K, rows, feature_dim_padded, sm_count);
+}
+
 int64_t ladine_debug_plan(int32_t K, int32_t rows, int32_t feature_dim_padded, int32_t geometry, int32_t row_major,
                           int32_t units, int32_t* table_out, int64_t cap, int32_t info_out[4]) {
   if (K < 1 || K > LADINE_MAX_GROUP || rows < 1 || feature_dim_padded < 256 || feature_dim_padded % 256 != 0 ||

@@ -112,6 +112,7 @@ cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int lay
 size_t sched_bytes_bound(int K, int rows, int NB);
 int64_t debug_plan(int K, int rows, int Fp, int geometry, int row_major, int units, int32_t* table_out, int64_t cap,
                    int32_t info_out[4]);
+int debug_geometry(int K, int rows, int Fp, int sm_count);
 size_t tensor_gemm_smem_bytes(int Cp);
 
 // ---- whole-chain persistent kernel for small calls (ladine_persist.cu) ----

@@ -20,8 +20,10 @@
 // Tile geometries (all bit-identical, chosen per call by choose_ctas): 128 x 256 single-CTA tiles, 256 x 256 CTA-pair
 // tiles (+ 2 x 64-row half tiles), slim 128 x 128 single-CTA tiles for calls too small to fill the SMs.  Tile order
 // (plan_tiles): N-tile-major while a member's activations fit in L2, row-major beyond.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <vector>
 
 #include "ladine_internal.cuh"
 #include "ladine_tc.cuh"
@@ -945,12 +947,24 @@ int choose_ctas(const ladine_handle* h, int K, int rows, int Fp) {
   const long long wide_tiles = (long long)K * ((rows + BM - 1) / BM) * (Fp / BN);
   if (h->ctas == kGeomSlim || (h->ctas == 0 && 2 * wide_tiles <= (long long)h->sm_count)) return kGeomSlim;
   if (h->ctas == 1 || h->ctas == 2) return h->ctas;
-  // cost in single-CTA 128-row tile times; a full pair tile (256 rows on 2 SMs) costs 2 / pair_gain, a half
-  // tile 1.7 / pair_gain (see plan_tiles).  Pairs must win by 3 % to be chosen (static-schedule quantisation).
+  // Makespan of the static schedule in single-CTA 128-row tile times, for both geometries on THIS many SMs (the tile
+  // counts quantise differently: one member x 1400 rows is 176 single tiles = 2 rounds on 148 SMs, but 80 pair tiles +
+  // 16 half tiles on 74 SM pairs = 2 pair rounds, each 1 / pair_gain as long -- while K = 5 x 1400 rows is 5.95 rounds
+  // of single tiles against 6.7 pair rounds).  A full pair tile (256 rows on 2 SMs) takes 1 / pair_gain, a half tile
+  // 0.85 / pair_gain (costs 20 : 17, as in plan_tiles, whose longest-processing-time deal is replayed here on counts).
+  // Pairs must win by 3 % to be chosen.
+  const long long per_col = (long long)K * (Fp / BN);
+  const int units2 = h->sm_count / 2 > 0 ? h->sm_count / 2 : 1;
   const int full2 = rows / 256, rem2 = rows - full2 * 256;
-  const double cost2 = (2.0 * full2 + (rem2 == 0 ? 0.0 : rem2 <= 128 ? 1.7 : 2.0)) / h->pair_gain;
-  const double cost1 = (rows + 127) / 128;
-  return cost2 * 1.03 < cost1 ? 2 : 1;
+  const long long n_full = per_col * (full2 + (rem2 > 128 ? 1 : 0)), n_half = per_col * (rem2 > 0 && rem2 <= 128 ? 1 : 0);
+  // full tiles dealt evenly (the first n_full % units2 units carry one more), half tiles to the least-loaded unit
+  std::vector<long long> load(units2);
+  for (int u = 0; u < units2; ++u) load[u] = (n_full / units2 + (u < n_full % units2 ? 1 : 0)) * 20;
+  for (long long i = 0; i < n_half; ++i) *std::min_element(load.begin(), load.end()) += 17;
+  const long long max_load = *std::max_element(load.begin(), load.end());
+  const double span2 = (double)max_load / 20.0 / h->pair_gain;
+  const double span1 = (double)((wide_tiles + h->sm_count - 1) / h->sm_count);
+  return span2 * 1.03 < span1 ? 2 : 1;
 }
 
 // One lane = one group of members advancing through the reverse steps on its own stream.  Lanes are
@@ -1189,6 +1203,12 @@ int64_t debug_plan(int K, int rows, int Fp, int geometry, int row_major, int uni
   const int64_t n = (int64_t)plan.table.size();
   if (n <= cap && table_out) std::copy(plan.table.begin(), plan.table.end(), table_out);
   return n;
+}
+
+int debug_geometry(int K, int rows, int Fp, int sm_count) {
+  ladine_handle tmp;   // default options: auto geometry, default pair gain
+  tmp.sm_count = sm_count;
+  return choose_ctas(&tmp, K, rows, Fp);
 }
 
 cudaError_t launch_debug_layer(ladine_handle* h, const ladine_member* m, int layer, int t, const void* h_in, int rows,

@@ -97,7 +97,7 @@ def _prepare(model, x, y_0_hat, y_T_mean, output_detach, precision):
                                   "inputs requiring grad); the reference only samples under torch.no_grad()")
     if getattr(model, "training", False):
         raise NotImplementedError("model.train() (batch-statistics BatchNorm) is not accelerated: call model.eval()")
-    device = next(model.parameters()).device
+    device = model.device if isinstance(model, engine.PackedModel) else next(model.parameters()).device
     pm = engine.packed_member_of(model, precision)
     for name, t in (("x", x), ("y_0_hat", y_0_hat), ("y_T_mean", y_T_mean)):
         if t.device != device:

@@ -165,6 +165,8 @@ _CHECKSUM_SAMPLES = 4096
 
 
 def _select(model, trunk: bool):
+    if isinstance(model, PackedModel):
+        return []                      # packed form only: immutable, nothing to fingerprint
     sd = model.state_dict(keep_vars=True)
     return [(k, v) for k, v in sd.items() if v.is_floating_point() and k.startswith(("lin", "unetnorm")) == trunk]
 

@@ -562,6 +562,11 @@ def test_packed_images_round_trip_and_refuse_damage(name, prec):
     assert torch.equal(yc3, ya)
     with pytest.raises(ValueError):
         engine.packed_member_of(packed, "bf16" if prec != "bf16" else "fp16")
+    from nested_diffusion_b200 import diffusion_utils as du     # ... and so does the drop-in p_sample_loop
+    with torch.no_grad():
+        yd = du.p_sample_loop(packed, xc, yc, yc, m["T"], alphas, omabs, only_last_sample=True, noise=noise.cuda(),
+                              precision=prec, persistent=False)
+    assert torch.equal(yd, ya[0, 0])
 
     bad = img_m.clone()
     bad[img_m.numel() // 2] ^= 0x40

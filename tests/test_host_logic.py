@@ -116,6 +116,22 @@ def test_static_tile_schedule_covers_every_tile_once_and_balances(K, rows, Fp, g
             assert len({f[1] for f in first}) <= -(-len(table) // row_tiles) + 1
 
 
+@pytest.mark.parametrize("K,rows,want,why", [
+    (5, 20480, 2, "config 3: 87 single rounds vs 87 pair rounds, each 1/1.08 as long"),
+    (5, 2560, 2, "an 8-GPU shard of config 3"),
+    (5, 1400, 1, "config 2: 5.95 rounds of single tiles vs 6.7 pair rounds (measured 205 vs 210 us)"),
+    (1, 1400, 2, "one member x 1400 rows (draws-ahead): 176 single tiles = 2 rounds on 148 SMs, 96 pair units = 2 shorter ones"),
+    (1, 64, 3, "config 1: 16 wide tiles -> slim tiles still fit one round"),
+    (1, 128, 3, "one row tile"),
+    (2, 128, 3, "two members x one row tile: 32 wide tiles, 64 slim ones"),
+    (5, 128, 1, "80 wide tiles: two rounds of slim ones -> wide"),
+])
+def test_auto_geometry_choice(K, rows, want, why):
+    lib = _capi.load()
+    assert lib.ladine_debug_geometry(K, rows, 4096, 148) == want, why
+    assert lib.ladine_debug_geometry(0, rows, 4096, 148) < 0 and lib.ladine_debug_geometry(K, rows, 100, 148) < 0
+
+
 def test_debug_plan_rejects_bad_arguments():
     lib = _capi.load()
     info = (ctypes.c_int32 * 4)()
