@@ -87,9 +87,19 @@ class EnsembleResult:
 class NestedEnsemble:
     """K packed members kept resident on one GPU (no per-batch CPU<->GPU shuttle)."""
 
+    # Chains (images x draws) per member per ladine_sample call.  Bounds the activation workspace (2 x rows x F 16-bit per
+    # member) AND keeps the GEMM launches short enough for the L2: the CTAs of a launch walk a static tile schedule at
+    # their own pace, and over a very long launch they drift apart until the 16 column tiles that share an activation row
+    # tile (and the row tiles that share a weight tile) no longer meet in L2 -- measured DRAM reads per row of a layer-2
+    # launch: 19 KB at 20 480 rows per member, 37 KB at 163 840, 52 KB at 256 000 (8 KB algorithmic), and under the 1 kW
+    # cap that traffic costs clock: 27.5 -> 29.8 -> 32.7 ns per row.  Measured optimum (profiles/README.md): 32 768 --
+    # the 5.12 M-chain sweep point runs at 18.4 k samples/s with it against 15.8-16.1 k at the round-1 cap of 262 144;
+    # config 3 (20 480 rows per member) stays one call, and smaller caps lose again (more, shorter launches).
+    MAX_ROWS_PER_CALL = 32768
+
     def __init__(self, models: Sequence, precision: str = "auto", member_ids: Optional[Sequence[int]] = None,
-                 max_rows_per_call: int = 262144):
-        self.max_rows_per_call = int(max_rows_per_call)  # chains (images x draws) per member per launch group
+                 max_rows_per_call: Optional[int] = None):
+        self.max_rows_per_call = int(max_rows_per_call if max_rows_per_call is not None else self.MAX_ROWS_PER_CALL)
         if len(models) < 1:
             raise ValueError("need at least one member")
         self.models = list(models)
@@ -130,9 +140,10 @@ class NestedEnsemble:
         coef = coef_table(alphas, one_minus_alphas_bar_sqrt, n_steps)
         n = xf.shape[1]
         total = images_total if images_total else n
-        # bound the activation workspace (2 x rows x F 16-bit per member): process image tiles in turn;
+        # bound the rows per call (workspace and L2 locality, see MAX_ROWS_PER_CALL): process image tiles in turn;
         # Philox ids are global, so tiling does not change a single sample
-        tile = max(1, min(n, self.max_rows_per_call // max(1, int(draws))))
+        cap = max(1, min(n, self.max_rows_per_call // max(1, int(draws))))
+        tile = -(-n // -(-n // cap)) if n else 1          # equal tiles: no small remainder call
         ys, ps = [], []
         for lo in range(0, n, tile):
             hi = min(n, lo + tile)

@@ -32,7 +32,7 @@ def member(seed, T):
 def run(T, D, N, k=K, budget_rowsteps=7e8):
     members = [nd.PackedMember(member(s, T), n_steps=T, precision="fp16") for s in range(k)]
     ens = nd.NestedEnsemble.__new__(nd.NestedEnsemble)
-    ens.members, ens.member_ids, ens.device, ens.models, ens.max_rows_per_call = members, list(range(k)), dev, [], 262144
+    ens.members, ens.member_ids, ens.device, ens.models, ens.max_rows_per_call = members, list(range(k)), dev, [], nd.NestedEnsemble.MAX_ROWS_PER_CALL
     g = torch.Generator(device="cuda").manual_seed(0)
     xf = torch.randn(k, N, F, device=dev, generator=g)
     yh = torch.softmax(torch.randn(k, N, C, device=dev, generator=g), -1)

@@ -37,7 +37,8 @@ class FeatureEnsemble(nd.NestedEnsemble):
 
     def __init__(self, members, xf):
         self.members, self.member_ids, self.device = members, list(range(len(members))), dev
-        self.models, self.max_rows_per_call, self.xf = [], 262144, xf
+        self.models, self.xf = [], xf
+        self.max_rows_per_call = int(os.environ.get("LADINE_MAX_ROWS", nd.NestedEnsemble.MAX_ROWS_PER_CALL))   # A/B of the row cap
 
     def encode(self, xx):
         lo = int(xx[0, 0].item())
@@ -102,6 +103,10 @@ def run(T, D, N, budget_rowsteps=float(os.environ.get("SWEEP_BUDGET", "7e8")), r
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "points":      # python tools/sweep_dist.py points T,D,N [T,D,N ...]
+        for spec in sys.argv[2:]:
+            run(*[int(v) for v in spec.split(",")])
+        sys.exit(0)
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
     for T in (100, 1000):
         for D in (10, 100, 1000):
