@@ -141,7 +141,12 @@ int ladine_free_member(ladine_handle* h, ladine_member* m);
 uint64_t ladine_member_bytes(const ladine_member* m);
 int ladine_member_precision(const ladine_member* m);
 
-/* The hot path.  members: HOST array of K packed members with identical F, C, T, precision. */
+/* The hot path.  members: HOST array of K packed members with identical F, C, T, precision.
+ * Sizing note: the throughput per chain is flat from ~6 000 to ~80 000 chains (N x D) per member per call and falls beyond
+ * (-8 % at 164 000, -19 % at 256 000: the CTAs of one very long GEMM launch drift apart in their static tile lists and the
+ * tiles that share operands stop meeting in L2).  Callers with more chains should split the images over several calls --
+ * image_offset / images_total keep the Philox streams, hence the samples, identical; the Python NestedEnsemble does this
+ * at 32 768 chains per member. */
 int ladine_sample(ladine_handle* h, const ladine_member* const* members, const ladine_sample_args* args);
 
 /* Write the N(0,1) draws ladine_sample would generate itself for (seed, chain ids) into
