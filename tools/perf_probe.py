@@ -19,6 +19,10 @@ tail_vec = int(sys.argv[11]) if len(sys.argv) > 11 else 0
 engine.set_option(0, "tail_vec", tail_vec)
 order = int(sys.argv[12]) if len(sys.argv) > 12 else 0
 engine.set_option(0, "order", order)
+import os
+for kv in os.environ.get("LADINE_OPTIONS", "").split(","):   # e.g. LADINE_OPTIONS=pace=2
+    if "=" in kv:
+        engine.set_option(0, kv.split("=")[0], int(kv.split("=")[1]))
 C = 2
 dev = torch.device("cuda")
 g = torch.Generator(device="cuda").manual_seed(0)
