@@ -742,7 +742,7 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
   const uint64_t lane_base = off;
   uint64_t lo = 0;
   const uint64_t o_u = lo; lo = align_up(lo + (uint64_t)gmax * a->N * Fp * 4, 1024);
-  uint64_t o_h1 = 0, o_h2 = 0, o_part = 0, o_y = 0, o_sched = 0, o_arr = 0, o_pace = 0;
+  uint64_t o_h1 = 0, o_h2 = 0, o_part = 0, o_y = 0, o_sched = 0, o_arr = 0;
   if (tensor) {
     o_h1 = lo; lo = align_up(lo + m_total * act_cols * 2, 1024);
     o_h2 = lo; lo = align_up(lo + m_total * act_cols * 2, 1024);
@@ -750,7 +750,6 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
     o_sched = lo; lo = align_up(lo + sched_bytes_bound(gmax, rows, Fp / 128), 1024);
     o_arr = lo; lo = align_up(lo + (uint64_t)gmax * ((rows + 127) / 128 + 1) * 2 * sizeof(int), 1024);
     o_y = lo; lo = align_up(lo + 2 * m_total * Cp * 4, 1024);
-    o_pace = lo; lo = align_up(lo + 64, 1024);
   }
   const uint64_t lane_bytes = lo;
   rc = ensure_workspace(h, lane_base + lane_bytes * lanes);
@@ -818,7 +817,6 @@ int ladine_sample(ladine_handle* h, const ladine_member* const* members, const l
         tw.u = d_u;
         tw.sched = reinterpret_cast<int32_t*>(lw + o_sched);
         tw.arrivals = reinterpret_cast<int*>(lw + o_arr);
-        tw.pace = reinterpret_cast<unsigned long long*>(lw + o_pace);
         std::string err;
         chains[l] = tensor_chain_create(h, members + k0, g, ids, h_coef, tw, si.n_slots, si.n_traj, ls,
                                         /*single_lane=*/nl == 1, &h->last_launches, &err, &e);
@@ -873,11 +871,6 @@ int ladine_set_option(ladine_handle* h, const char* key, int64_t value) {
   if (strcmp(key, "order") == 0) {
     if (value < 0 || value > 2) return fail(h, LADINE_ERR_INVALID, "order must be 0 (auto), 1 (N-tile-major) or 2 (row-major)");
     h->order = (int)value;
-    return LADINE_OK;
-  }
-  if (strcmp(key, "pace") == 0) {
-    if (value < 0 || value > 64) return fail(h, LADINE_ERR_INVALID, "pace must be in [0, 64]");
-    h->pace = (int)value;
     return LADINE_OK;
   }
   if (strcmp(key, "tail_vec") == 0) {

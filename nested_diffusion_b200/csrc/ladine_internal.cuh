@@ -67,7 +67,6 @@ struct ladine_handle {
   int ctas = 0;             // 0 = choose per call, 1 = cta_group::1, 2 = cta_group::2 CTA pairs
   int order = 0;             // GEMM tile order: 0 = auto, 1 = N-tile-major, 2 = row-major
   int tail_vec = 0;          // tail/head features per thread: 0 = pick by wave quantisation, else 4 or 8
-  int pace = 0;              // GEMM pacing slack in tiles (0 = off): see GemmParams::pace
   double pair_gain = 1.08;   // measured throughput ratio pair/single per useful tile (see choose_ctas)
   cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};  // [0] unused: caller's stream
   // end of the last ladine_sample / ladine_encode on this handle: the next call's stream waits for it before it touches
@@ -100,7 +99,6 @@ struct TensorWorkspace {
   float* u;      // [K, N, Fp]
   int32_t* sched;  // static tile schedules of this lane's GEMM launches (layer 2 | layer 3)
   int* arrivals;   // row-group arrival counters of the fused tail + head
-  unsigned long long* pace;   // [2] tile-start counters of the lane's layer-2 / layer-3 launches (option "pace")
 };
 struct TensorChain;  // one lane: a group of members advancing through the reverse steps on one stream
 TensorChain* tensor_chain_create(ladine_handle* h, const ladine_member* const* members, const ladine_sample_args& a,

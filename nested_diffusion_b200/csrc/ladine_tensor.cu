@@ -265,23 +265,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) trunk_gemm_kernel(const __gri
         const int32_t code = __ldg(my_sched + it);
         if (code < 0) break;
         const TileCode tc(code);
-        if (p.pace != nullptr) {
-          // pacing: do not run more than pace_slack tiles ahead of the launch's average (see GemmParams::pace)
-          if (it > p.pace_slack && it - p.pace_slack <= p.pace_min_len) {
-            const unsigned long long target = p.pace_base + (unsigned long long)(it - p.pace_slack) * gridDim.x;
-            const volatile unsigned long long* ctr = p.pace;
-            if (*ctr < target) {
-              const long long t0 = clock64();
-              while (*ctr < target) {
-                if (clock64() - t0 > 4000000000LL) {
-                  printf("ladine: pacing timeout block=%d it=%d seen=%llu target=%llu\n", (int)blockIdx.x, it, *ctr, target);
-                  __trap();
-                }
-              }
-            }
-          }
-          atomicAdd(p.pace, 1ULL);   // result unused: a fire-and-forget reduction
-        }
         // a half tile gives each CTA of the pair 64 rows; the 128-row box is still loaded (upper half unused)
         const int arow = tc.member * p.rows_pad + tc.mb * (BM * CTAS) + (int)rank * (tc.half ? BM / 2 : BM);
         const int brow = tc.nb * BNT + (int)rank * Cfg::kBRows;
@@ -999,7 +982,6 @@ struct TensorChain {
   dim3 tgrid;
   int grid = 0, K = 0, Fp = 0, Cp = 0, slot_base = 0, ctas = 1, ycur = 0, g3_launches = 0, tail_vec = 8;
   bool fuse = false, split = false;
-  unsigned long long pace_adds2 = 0, pace_adds3 = 0, pace_n2 = 0, pace_n3 = 0;   // pacing: counter adds per launch, launches so far
   float* ybuf[2] = {nullptr, nullptr};
   bool bf16 = false;
 
@@ -1079,30 +1061,6 @@ struct TensorChain {
       g->idesc_half = make_idesc(bf16, 1);  // M = 128 across the pair
       g->fuse = 0;
     }
-    // pacing ("pace" option; 16-bit tile kernels only)
-    pace_adds2 = pace_adds3 = 0;
-    pace_n2 = pace_n3 = 0;
-    if (h->pace > 0 && !split && ws.pace != nullptr) {
-      e = cudaMemsetAsync(ws.pace, 0, 2 * sizeof(unsigned long long), st);
-      if (e != cudaSuccess) return e;
-      auto census = [&](const TilePlan& pl, GemmParams* g, unsigned long long* adds) {
-        int min_len = pl.stride;
-        unsigned long long total = 0;
-        for (int u = 0; u < pl.units; ++u) {
-          int len = 0;
-          while (len < pl.stride && pl.table[(size_t)u * pl.stride + len] >= 0) ++len;
-          min_len = len < min_len ? len : min_len;
-          total += (unsigned long long)len;
-        }
-        *adds = total * (unsigned long long)cpu;   // every CTA of a unit counts its own tile starts
-        g->pace_slack = h->pace;
-        g->pace_min_len = min_len;
-      };
-      census(plan, &g2, &pace_adds2);
-      census(plan3, &g3, &pace_adds3);
-      g2.pace = ws.pace;
-      g3.pace = ws.pace + 1;
-    }
     g3.sched = sched3;
     g3.sched_stride = plan3.stride;
     g3.fuse = fuse ? 1 : 0;
@@ -1177,8 +1135,6 @@ struct TensorChain {
       g3.shift[k] = members[k]->Cc[2] + (size_t)t * Fp;
     }
     cudaError_t e;
-    g2.pace_base = pace_adds2 * pace_n2++;
-    g3.pace_base = pace_adds3 * pace_n3++;
     {
       ProfSpan ps(h, st, 0);
       e = split ? launch_split_gemm(2, g2, grid, Cp, st) : launch_gemm<2>(g2, grid, bf16, Cp, ctas, st);

@@ -59,15 +59,6 @@ struct GemmParams {
   // entry = member << 23 | nb << 13 | mb << 1 | half   (half: CTA-pair tile of 2 x 64 rows, M=128 MMAs)
   const int32_t* sched;
   int sched_stride;
-  // ---- pacing (option "pace" = slack in tiles, 0 = off) ----
-  // The CTAs of a launch walk their static lists at their own pace; over long lists they drift apart and the tiles that
-  // share operands stop meeting in L2.  With pacing every producer counts its tile starts into one global counter and
-  // does not start its tile `it` before the launch as a whole has started (it - slack) tiles per CTA: nobody runs more
-  // than ~slack tiles ahead of the average.  The counter runs on over the launches of a chain (pace_base).
-  unsigned long long* pace;            // null: off
-  unsigned long long pace_base;        // counter value when this launch starts
-  int pace_slack;
-  int pace_min_len;                    // shortest list of the schedule: the check is skipped beyond it
   uint32_t idesc;                      // full tiles: M = 128 * CTAS
   uint32_t idesc_half;                 // pair half tiles: M = 128 (64 rows per CTA)
   // ---- layer 3 with the tail + head fused in (fuse != 0) ----
