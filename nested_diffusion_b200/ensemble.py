@@ -145,7 +145,7 @@ class NestedEnsemble:
         cap = max(1, min(n, self.max_rows_per_call // max(1, int(draws))))
         tile = -(-n // -(-n // cap)) if n else 1          # equal tiles: no small remainder call
         ys, ps = [], []
-        for lo in range(0, n, tile):
+        for lo in range(0, max(n, 1), tile):   # n == 0: one (empty) call, so that the result has its shape
             hi = min(n, lo + tile)
             out = engine.sample_chains(
                 self.members, xf[:, lo:hi], y0hats[:, lo:hi], mus[:, lo:hi], coef, draws,

@@ -650,6 +650,9 @@ def test_empty_and_single_row_batches():
         one = du.p_sample_loop(model, xc[2:3], yc[2:3], yc[2:3], m["T"], alphas, omabs, only_last_sample=True,
                                noise=nc[:, 2:3])
         assert rel_err(one[0].cpu(), full[2].cpu()) <= 1e-6   # rows are independent: same arithmetic per row
+        import nested_diffusion_b200 as nd                    # the batched API on an empty batch keeps its shapes
+        res = nd.NestedEnsemble([model]).sample(xc[:0], yc[None, :0], 3, m["T"], alphas, omabs, seed=1, temperature=0.2)
+        assert tuple(res.y0.shape) == (1, 3, 0, m["C"]) and tuple(res.probs.shape) == (1, 3, 0, m["C"])
 
 
 @pytest.mark.slow
