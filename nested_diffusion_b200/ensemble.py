@@ -46,6 +46,18 @@ def weighted_bounds(n_items: int, weights: Sequence[float]) -> List[Tuple[int, i
     return [(edges[i], edges[i + 1]) for i in range(len(w))]
 
 
+def image_tiles(n_images: int, draws: int, max_rows: int) -> List[Tuple[int, int]]:
+    """Split ``range(n_images)`` into the fewest contiguous tiles of at most ``max_rows // draws`` images (at least one
+    image per tile), all of (nearly) equal size so that no small remainder call is left; an empty batch is one empty
+    tile (the call still has to produce its empty outputs)."""
+    if n_images <= 0:
+        return [(0, 0)]
+    cap = max(1, min(n_images, int(max_rows) // max(1, int(draws))))
+    n_tiles = -(-n_images // cap)
+    tile = -(-n_images // n_tiles)
+    return [(lo, min(n_images, lo + tile)) for lo in range(0, n_images, tile)]
+
+
 def gather_image_shards(local: torch.Tensor, n_items: int, group=None,
                         bounds: Optional[Sequence[Tuple[int, int]]] = None) -> torch.Tensor:
     """All-gather per-rank tensors ``[n_local, ...]`` (image-major) into ``[n_items, ...]`` on every rank.
@@ -142,11 +154,8 @@ class NestedEnsemble:
         total = images_total if images_total else n
         # bound the rows per call (workspace and L2 locality, see MAX_ROWS_PER_CALL): process image tiles in turn;
         # Philox ids are global, so tiling does not change a single sample
-        cap = max(1, min(n, self.max_rows_per_call // max(1, int(draws))))
-        tile = -(-n // -(-n // cap)) if n else 1          # equal tiles: no small remainder call
         ys, ps = [], []
-        for lo in range(0, max(n, 1), tile):   # n == 0: one (empty) call, so that the result has its shape
-            hi = min(n, lo + tile)
+        for lo, hi in image_tiles(n, draws, self.max_rows_per_call):
             out = engine.sample_chains(
                 self.members, xf[:, lo:hi], y0hats[:, lo:hi], mus[:, lo:hi], coef, draws,
                 noise=None if noise is None else noise[:, :, :, lo:hi], seed=seed or 0, member_ids=self.member_ids,

@@ -375,6 +375,24 @@ def test_shard_bounds_partition():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_image_tiles_are_equal_and_cover_the_batch():
+    """NestedEnsemble's rows-per-call cap (32 768 rows per member: longer launches lose L2 locality)."""
+    from nested_diffusion_b200.ensemble import NestedEnsemble, image_tiles
+
+    assert NestedEnsemble.MAX_ROWS_PER_CALL == 32768
+    assert image_tiles(1024, 20, 32768) == [(0, 1024)]                              # config 3: one call
+    assert image_tiles(16384, 10, 32768) == [(i * 2731, min(16384, (i + 1) * 2731)) for i in range(6)]
+    assert image_tiles(1024, 1000, 32768) == [(i * 32, (i + 1) * 32) for i in range(32)]
+    assert image_tiles(3, 100000, 32768) == [(0, 1), (1, 2), (2, 3)]                # draws beyond the cap: one image per call
+    assert image_tiles(0, 20, 32768) == [(0, 0)]
+    for n, d, cap in ((70, 20, 32768), (10, 3, 10), (977, 7, 500), (5, 1, 1)):
+        tiles = image_tiles(n, d, cap)
+        assert tiles[0][0] == 0 and tiles[-1][1] == n and all(a[1] == b[0] for a, b in zip(tiles, tiles[1:]))
+        sizes = [b - a for a, b in tiles]
+        assert max(sizes) * d <= max(cap, d) and max(sizes) - min(sizes) <= max(1, len(tiles) - 1)
+        assert len(tiles) == -(-n // max(1, min(n, cap // d)))                      # the fewest tiles the cap allows
+
+
 def test_weighted_bounds_partition():
     """Speed-weighted image tiles: contiguous, exhaustive, proportional; degenerate weights give empty tiles, not errors."""
     for n in (1, 7, 70, 1024):
