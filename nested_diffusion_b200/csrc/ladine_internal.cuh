@@ -66,7 +66,7 @@ struct ladine_handle {
   bool persist_debug = false;   // block 0 of the persistent kernel prints its per-phase clock totals
   int ctas = 0;             // 0 = choose per call, 1 = cta_group::1, 2 = cta_group::2 CTA pairs
   int order = 0;             // GEMM tile order: 0 = auto, 1 = N-tile-major, 2 = row-major
-  int tail_vec = 0;          // tail/head features per thread: 0 = pick by wave quantisation, else 4 or 8
+  int tail_vec = 0;          // tail/head features per thread: 0 = default (4), else 4 or 8 (A/B timing)
   double pair_gain = 1.08;   // measured throughput ratio pair/single per useful tile (see choose_ctas)
   cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};  // [0] unused: caller's stream
   // end of the last ladine_sample / ladine_encode on this handle: the next call's stream waits for it before it touches
