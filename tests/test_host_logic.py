@@ -522,3 +522,32 @@ def test_packed_cache_key_follows_content_not_name(tmp_path):
     _write_image(str(tmp_path / "i.ladine"), img)
     assert torch.equal(_read_image(str(tmp_path / "i.ladine")), img)
     assert [p.name for p in tmp_path.iterdir() if ".tmp" in p.name] == []
+
+
+def test_cache_validity_rules_on_cpu_tensors():
+    """engine._Cached (the rule behind the pack / encoder / feature caches) and diffusion_utils._tensor_key (draws-ahead):
+    an in-place edit invalidates, a storage swap with the same values (the runner's CPU<->GPU shuttle) does not, a
+    storage swap with new values does."""
+    from nested_diffusion_b200 import diffusion_utils as du
+    from nested_diffusion_b200 import engine
+
+    lin = torch.nn.Linear(64, 32)
+    tensors = lambda: [(k, v) for k, v in lin.state_dict(keep_vars=True).items()]
+    c = engine._Cached(tensors(), "fp16", "packed")
+    assert c.valid_for(tensors(), "fp16") and not c.valid_for(tensors(), "bf16")
+    lin.weight.data = lin.weight.data.clone()                      # new storage, same values
+    assert c.valid_for(tensors(), "fp16")
+    lin.bias.data = lin.bias.data + 1.0                            # new storage, new values, no version bump
+    assert not c.valid_for(tensors(), "fp16")
+    c = engine._Cached(tensors(), "fp16", "packed")
+    with torch.no_grad():
+        lin.weight.mul_(1.5)                                       # in-place: version counter
+    assert not c.valid_for(tensors(), "fp16")
+
+    x = torch.randn(6, 4)
+    k0 = du._tensor_key(x)
+    assert du._tensor_key(x) == k0 and du._tensor_key(x[:]) == k0  # a fresh view of the same data is the same input
+    assert du._tensor_key(x[1:]) != k0 and du._tensor_key(x.clone()) != k0
+    x.add_(1.0)
+    assert du._tensor_key(x) != k0                                 # in-place change
+    assert du.set_draws_ahead(20) == 0 and du.set_draws_ahead(0) == 20
