@@ -428,6 +428,53 @@ assert torch.equal(got_w, full), "weighted shards gather differently"
 mv = stats.majority_voting_for_mc_samples(got.permute(1, 0, 2))
 ref = stats.majority_voting_for_mc_samples(full.permute(1, 0, 2))
 assert torch.equal(mv, ref)
+# the whole sharded entry point (host logic of config 4) with a stub ensemble whose "samples" are a pure function of the
+# GLOBAL (member, draw, image) ids -- as the Philox streams are: any partition must gather to the single-process result
+from nested_diffusion_b200.ensemble import EnsembleResult, NestedEnsemble, image_tiles
+
+class Stub(NestedEnsemble):
+    def __init__(self, K):
+        self.members, self.models, self.member_ids = [None] * K, [], list(range(K))
+        self.device, self.precision, self.max_rows_per_call = torch.device("cpu"), "auto", 64
+        self.calls = []
+    @property
+    def K(self):
+        return len(self.members)
+    def sample(self, x, y0hats, draws, n_steps, alphas, omabs, *, seed=None, temperature=None, image_offset=0,
+               images_total=0, **kw):
+        self.calls.append((image_offset, x.shape[0], images_total))
+        K, N, C = len(self.members), x.shape[0], y0hats.shape[-1]
+        k = torch.arange(K).view(K, 1, 1, 1); d = torch.arange(draws).view(1, draws, 1, 1)
+        i = (torch.arange(N) + image_offset).view(1, 1, N, 1); c = torch.arange(C).view(1, 1, 1, C)
+        y = (seed + 1000.0 * k + 10.0 * d + 0.001 * i + 0.0001 * c + x[:, :1].view(1, 1, N, 1) + y0hats.unsqueeze(1)).float()
+        return EnsembleResult(y, torch.softmax(-y / temperature, -1) if temperature is not None else None,
+                              (image_offset, image_offset + N))
+
+K, D, C = 3, 4, 2
+x = torch.randn(n, 5, generator=g); yh = torch.softmax(torch.randn(K, n, C, generator=g), -1)
+ens = Stub(K)
+y0, probs = nd.sample_ensemble(ens, x, yh, D, 10, None, None, seed=7, temperature=0.5)
+lo, hi = nd.shard_bounds(n, rank, world)
+assert ens.calls == [(lo, hi - lo, n)], ens.calls                       # this rank sampled exactly its image tile
+single = Stub(K).sample(x, yh, D, 10, None, None, seed=7, temperature=0.5)
+want_y = single.y0.permute(2, 0, 1, 3).reshape(n, K * D, C)
+assert tuple(y0.shape) == (n, K * D, C) and torch.equal(y0, want_y)
+assert torch.equal(probs, single.probs.permute(2, 0, 1, 3).reshape(n, K * D, C))
+yw, _ = nd.sample_ensemble(Stub(K), x, yh, D, 10, None, None, seed=7, temperature=0.5, shard_weights=[1.0, 0.4])
+assert torch.equal(yw, want_y), "speed-weighted tiles must not change the gathered samples"
+y_none, p_none = nd.sample_ensemble(Stub(K), x, yh, D, 10, None, None, seed=7)
+assert torch.equal(y_none, want_y) and p_none is None
+# without a seed the ranks must agree on one (rank 0 draws it, broadcast): every rank ends with the same tensor
+torch.manual_seed(100 + rank)                                            # different local generators on purpose
+y_auto, _ = nd.sample_ensemble(Stub(K), x, yh, D, 10, None, None)
+both = [torch.empty_like(y_auto) for _ in range(world)]
+dist.all_gather(both, y_auto)
+assert all(torch.equal(b, both[0]) for b in both), "ranks sampled with different seeds"
+try:
+    nd.sample_ensemble(Stub(K), x, yh, D, 10, None, None, seed=7, shard_weights=[1.0])
+    raise SystemExit("shard_weights of the wrong length must raise")
+except ValueError:
+    pass
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 """
