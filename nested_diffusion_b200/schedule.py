@@ -49,12 +49,38 @@ def schedule_tensors(betas: torch.Tensor, schedule: str = "linear"):
     return alphas, one_minus_alphas_bar_sqrt
 
 
+_COEF_CACHE: list = []   # [(key, (alphas, omabs) strong refs, table)], most recent first
+_COEF_CACHE_SIZE = 8
+
+
+def _vec_key(t: torch.Tensor) -> tuple:
+    return (t.untyped_storage().data_ptr(), t.storage_offset(), tuple(t.shape), tuple(t.stride()), t._version, t.dtype,
+            str(t.device))
+
+
 def coef_table(alphas: torch.Tensor, one_minus_alphas_bar_sqrt: torch.Tensor, n_steps: int) -> torch.Tensor:
     """HOST FP32 [n_steps, 8]: inv_q, 1-q, s, gamma_0, gamma_1, gamma_2, sqrt(beta_hat), 0 per table index t.
 
-    Row 0 is the noiseless last step (only the first three entries are used)."""
+    Row 0 is the noiseless last step (only the first three entries are used).  The table (READ-ONLY for callers) is
+    remembered for the last few (alphas, one_minus_alphas_bar_sqrt, n_steps): the runner passes the same two device
+    vectors to every one of its K x 20 ``p_sample_loop`` calls per batch, and rebuilding the table means two
+    device->host copies, i.e. a stream synchronisation that would serialise back-to-back calls.  A hit needs the same
+    storages / views / in-place version counters (strong references are held, so an address cannot be recycled)."""
     if alphas.shape[0] < n_steps or one_minus_alphas_bar_sqrt.shape[0] < n_steps:
         raise ValueError("schedule vectors are shorter than n_steps")
+    key = (_vec_key(alphas), _vec_key(one_minus_alphas_bar_sqrt), int(n_steps))
+    for i, (k, _, table) in enumerate(_COEF_CACHE):
+        if k == key:
+            if i:
+                _COEF_CACHE.insert(0, _COEF_CACHE.pop(i))
+            return table
+    table = _coef_table(alphas, one_minus_alphas_bar_sqrt, int(n_steps))
+    _COEF_CACHE.insert(0, (key, (alphas, one_minus_alphas_bar_sqrt), table))
+    del _COEF_CACHE[_COEF_CACHE_SIZE:]
+    return table
+
+
+def _coef_table(alphas: torch.Tensor, one_minus_alphas_bar_sqrt: torch.Tensor, n_steps: int) -> torch.Tensor:
     a = alphas.detach()[:n_steps].to("cpu", torch.float32)
     s = one_minus_alphas_bar_sqrt.detach()[:n_steps].to("cpu", torch.float32)
     s_prev = torch.cat([s[:1], s[:-1]])

@@ -598,3 +598,23 @@ def test_cache_validity_rules_on_cpu_tensors():
     x.add_(1.0)
     assert du._tensor_key(x) != k0                                 # in-place change
     assert du.set_draws_ahead(20) == 0 and du.set_draws_ahead(0) == 20
+
+
+def test_coef_table_is_remembered_until_the_schedule_changes():
+    """schedule.coef_table caches per (alphas, one_minus_alphas_bar_sqrt, n_steps): no device->host copy (= stream
+    synchronisation) on every one of the runner's K x 20 calls; an in-place edit or another tensor recomputes."""
+    alphas, omabs = schedule.schedule_tensors(schedule.make_beta_schedule("linear", 50, 1e-4, 0.02))
+    t1 = schedule.coef_table(alphas, omabs, 50)
+    assert schedule.coef_table(alphas, omabs, 50) is t1
+    assert schedule.coef_table(alphas, omabs, 40) is not t1 and schedule.coef_table(alphas, omabs, 40).shape[0] == 40
+    assert schedule.coef_table(alphas, omabs, 50) is t1                       # still remembered
+    a2 = alphas.clone()
+    t2 = schedule.coef_table(a2, omabs, 50)
+    assert t2 is not t1 and torch.equal(t2, t1)
+    a2.mul_(0.999)                                                            # in-place: version counter
+    t3 = schedule.coef_table(a2, omabs, 50)
+    assert t3 is not t2 and not torch.equal(t3, t2)
+    assert torch.equal(t3, schedule._coef_table(a2, omabs, 50))
+    for i in range(20):                                                       # bounded: old entries fall out
+        schedule.coef_table(alphas.clone(), omabs, 50)
+    assert len(schedule._COEF_CACHE) <= schedule._COEF_CACHE_SIZE
