@@ -36,6 +36,34 @@ def test_library_exports_every_declared_symbol():
     assert lib.ladine_version() == 3
 
 
+def test_header_is_plain_c_and_a_c_caller_links(tmp_path):
+    """include/ladine.h must be consumable by a C compiler (the boundary is a C ABI: cgo / JNI / ctypes bind it), and a C
+    translation unit that references every declared function must link against the shared library (no compute calls)."""
+    import shutil
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    hdr = os.path.join(ROOT, "include", "ladine.h")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    names = sorted(set(re.findall(r"\b(ladine_[a-z0-9_]+)\s*\(", open(hdr).read())))
+    assert set(names) == set(_capi.SYMBOLS), set(names) ^ set(_capi.SYMBOLS)
+    src = tmp_path / "caller.c"
+    src.write_text('#include "ladine.h"\n#include <stdio.h>\nint main(void) {\n  const void* fns[] = {' +
+                   ", ".join(f"(const void*){n}" for n in names) +
+                   '};\n  printf("%d %d\\n", ladine_version(), (int)(sizeof fns / sizeof fns[0]));\n  return 0;\n}\n')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(_capi.lib_path())
+    r = subprocess.run([gcc, "-std=gnu99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                        "-l:libladine.so", f"-Wl,-rpath,{libdir}", "-Wl,--allow-shlib-undefined"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if r.returncode == 0:      # libcudart may be unresolvable outside the torch process on a CPU-only box: linking is the test
+        assert r.stdout.split() == [str(_capi.load().ladine_version()), str(len(names))]
+
+
 def test_struct_sizes_match_header_layout():
     # sizes the C side checks through struct_size: any drift is an error at call time, not corruption
     assert ctypes.sizeof(_capi.MemberDesc) == 8 * 4 + 8 * 8 + 15 * 8
@@ -618,3 +646,41 @@ def test_coef_table_is_remembered_until_the_schedule_changes():
     for i in range(20):                                                       # bounded: old entries fall out
         schedule.coef_table(alphas.clone(), omabs, 50)
     assert len(schedule._COEF_CACHE) <= schedule._COEF_CACHE_SIZE
+
+
+def test_partitions_property_based():
+    """shard_bounds / weighted_bounds / image_tiles on random sizes (hypothesis): contiguous, exhaustive, within their caps."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from nested_diffusion_b200.ensemble import image_tiles
+
+    @settings(max_examples=200, deadline=None)
+    @given(n=st.integers(0, 5000), world=st.integers(1, 16))
+    def shards(n, world):
+        spans = [nd.shard_bounds(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+        assert max(sizes) == nd.ensemble.padded_shard_size(n, world)
+
+    @settings(max_examples=200, deadline=None)
+    @given(n=st.integers(0, 5000), w=st.lists(st.floats(0.05, 4.0), min_size=1, max_size=16))
+    def weighted(n, w):
+        spans = nd.weighted_bounds(n, w)
+        assert len(spans) == len(w) and spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] and a[0] <= a[1] for a, b in zip(spans, spans[1:]))
+        assert all(abs((b - a) - n * wi / sum(w)) <= 1.0 for (a, b), wi in zip(spans, w))
+
+    @settings(max_examples=300, deadline=None)
+    @given(n=st.integers(0, 20000), d=st.integers(1, 2000), cap=st.integers(1, 70000))
+    def tiles(n, d, cap):
+        t = image_tiles(n, d, cap)
+        assert t[0][0] == 0 and t[-1][1] == n and all(a[1] == b[0] for a, b in zip(t, t[1:]))
+        if n:
+            per = max(1, min(n, cap // d))
+            sizes = [b - a for a, b in t]
+            assert min(sizes) >= 1 and max(sizes) <= per and len(t) == -(-n // per)
+            assert max(sizes) - min(sizes) <= len(t)        # (nearly) equal tiles: no small remainder call
+
+    shards(); weighted(); tiles()
