@@ -258,6 +258,14 @@ int ladine_member_import(ladine_handle* h, const void* host_src, uint64_t bytes,
 uint64_t ladine_encoder_image_bytes(const ladine_encoder* enc);
 int ladine_encoder_export(ladine_handle* h, const ladine_encoder* enc, void* host_dst, uint64_t capacity, void* stream);
 int ladine_encoder_import(ladine_handle* h, const void* host_src, uint64_t bytes, void* stream, ladine_encoder** out);
+/* Host-only inspection (no device, no handle): kind_out = 1 (member) / 2 (encoder), dims_out = the header's dimension
+ * words (member: F, Fp, C, Cp, T, guidance, precision, split; encoder: data_dim, hidden_dim, feature_dim, eps bits).
+ * Returns LADINE_OK for an intact image of this library's ABI / layout version, else LADINE_ERR_INVALID with the reason in
+ * *why_out (a static string).  Image layout: bytes 0..7 magic "LADINEM\0" / "LADINEE\0", u32 ABI version, u32 packed-layout
+ * version, 20 x i32 dimensions, u64 payload bytes, u64 checksum of the payload (ladine_image_checksum), header padded to
+ * 128 bytes, then the packed buffers, each padded to 16 bytes. */
+int ladine_image_info(const void* host_src, uint64_t bytes, int32_t* kind_out, int32_t dims_out[20], const char** why_out);
+uint64_t ladine_image_checksum(const void* host_src, uint64_t bytes);
 /* dimensions of a packed object (what a wrapper needs after an import):
  * member  -> dims_out[6] = {feature_dim, num_classes, n_steps, guidance, precision, device}
  * encoder -> dims_out[4] = {data_dim, hidden_dim, feature_dim, device} */

@@ -82,6 +82,9 @@ SYMBOLS = {
     "ladine_encoder_image_bytes": (C.c_uint64, [C.c_void_p]),
     "ladine_encoder_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "ladine_encoder_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ladine_image_info": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_char_p)]),
+    "ladine_image_checksum": (C.c_uint64, [C.c_void_p, C.c_uint64]),
     "ladine_member_dims": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "ladine_encoder_dims": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "ladine_debug_geometry": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

@@ -567,6 +567,28 @@ static std::vector<ImageSection> member_sections(ladine_member* m) {
   return s;
 }
 
+// Host-only inspection of a packed image (needs no device or handle): what kind it is and whether it is intact.
+int ladine_image_info(const void* host_src, uint64_t bytes, int32_t* kind_out, int32_t dims_out[20], const char** why_out) {
+  static const char* const kOk = "";
+  if (why_out) *why_out = kOk;
+  if (kind_out) *kind_out = 0;
+  const ImageHeader* hd = nullptr;
+  const char* why = image_check(host_src, bytes, "LADINEM", &hd);
+  int kind = 1;
+  if (why && host_src && bytes >= kImageHeaderBytes && std::strncmp(static_cast<const char*>(host_src), "LADINEE", 8) == 0) {
+    why = image_check(host_src, bytes, "LADINEE", &hd);
+    kind = 2;
+  }
+  if (why) {
+    if (why_out) *why_out = why;
+    return LADINE_ERR_INVALID;
+  }
+  if (kind_out) *kind_out = kind;
+  if (dims_out) std::memcpy(dims_out, hd->dims, sizeof hd->dims);
+  return LADINE_OK;
+}
+uint64_t ladine_image_checksum(const void* host_src, uint64_t bytes) { return host_src ? image_checksum(host_src, bytes) : 0; }
+
 uint64_t ladine_member_image_bytes(const ladine_member* m) {
   if (!m) return 0;
   uint64_t total = kImageHeaderBytes;

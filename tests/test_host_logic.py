@@ -684,3 +684,45 @@ def test_partitions_property_based():
             assert max(sizes) - min(sizes) <= len(t)        # (nearly) equal tiles: no small remainder call
 
     shards(); weighted(); tiles()
+
+
+def test_packed_image_header_checks_without_a_device():
+    """ladine_image_info (host only): an image built to the documented layout is accepted; a flipped payload byte, a
+    truncated buffer, another layout version, a foreign magic and a too-short buffer are refused with a reason."""
+    import struct
+
+    lib = _capi.load()
+
+    def image(magic=b"LADINEM", layout=1, abi=None, payload=None, dims=(256, 256, 2, 2, 200, 1, 2, 0)):
+        payload = np.arange(4096, dtype=np.uint8).tobytes() * 3 if payload is None else payload
+        buf = np.zeros(128 + len(payload), dtype=np.uint8)
+        buf[128:] = np.frombuffer(payload, dtype=np.uint8)
+        ck = lib.ladine_image_checksum(buf[128:].ctypes.data, len(payload))
+        hdr = struct.pack("<8sII20iQQQ", magic, lib.ladine_version() if abi is None else abi, layout,
+                          *(list(dims) + [0] * (20 - len(dims))), len(payload), ck, 0)
+        assert len(hdr) == 120
+        buf[:120] = np.frombuffer(hdr, dtype=np.uint8)
+        return buf
+
+    def info(buf, n=None):
+        kind, dims, why = ctypes.c_int32(), (ctypes.c_int32 * 20)(), ctypes.c_char_p()
+        rc = lib.ladine_image_info(buf.ctypes.data, len(buf) if n is None else n, ctypes.byref(kind), dims, ctypes.byref(why))
+        return rc, kind.value, list(dims), (why.value or b"").decode()
+
+    rc, kind, dims, why = info(image())
+    assert (rc, kind, dims[:8], why) == (0, 1, [256, 256, 2, 2, 200, 1, 2, 0], "")
+    rc, kind, dims, _ = info(image(magic=b"LADINEE", dims=(300, 128, 256, 0)))
+    assert (rc, kind, dims[:3]) == (0, 2, [300, 128, 256])
+    bad = image()
+    bad[128 + 1000] ^= 0x10
+    assert info(bad)[0] < 0 and "checksum" in info(bad)[3]
+    assert info(image(), n=128 + 4096)[0] < 0 and "truncated" in info(image(), n=128 + 4096)[3]
+    assert "different library version" in info(image(layout=2))[3]
+    assert "different library version" in info(image(abi=lib.ladine_version() + 1))[3]
+    assert info(image(magic=b"NOTLADN"))[0] < 0 and "magic" in info(image(magic=b"NOTLADN"))[3]
+    assert info(image(), n=64)[0] < 0 and "shorter" in info(image(), n=64)[3]
+    # the checksum depends on every byte and on the length
+    a = np.arange(1000, dtype=np.uint8)
+    c0 = lib.ladine_image_checksum(a.ctypes.data, 1000)
+    b = a.copy(); b[999] ^= 1
+    assert lib.ladine_image_checksum(b.ctypes.data, 1000) != c0 and lib.ladine_image_checksum(a.ctypes.data, 999) != c0
